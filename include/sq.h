@@ -1,0 +1,193 @@
+/*
+ * sq.h -- C-ABI of libsq, the B200-native (sm_100a) replacement for StochQuant's
+ * device side: the OpenCL kernel `time_dev` (/root/reference/tau_kernel.cl:25-175,
+ * helpers :184-284) and the OpenCL plumbing that drives it from the host
+ * (/root/reference/tauhost.c:187-481 setup, :481-554 per-frame launch/transfers,
+ * :587-612 teardown).
+ *
+ * The reference exposes no library API: its boundary is the `tauhost.o` process
+ * (argv, stdout, start/end files).  `host/tauhost.c` in this repo keeps that
+ * boundary byte-compatible and calls the four entry points BASELINE.json names:
+ * sq_init / sq_step / sq_measure / sq_free.  Everything here is extern "C",
+ * plain pointers and sizes; the caller owns host memory, the library owns device
+ * memory and its stream.  All functions return SQ_OK (0) or a negative error
+ * code; nothing throws or aborts across the boundary.  A context is not
+ * thread-safe; use one per host thread.  There is NO CPU fallback: without a
+ * usable CUDA device sq_init fails with SQ_ERR_NODEVICE.
+ */
+#ifndef SQ_H
+#define SQ_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQ_API_VERSION 1
+
+/* error codes */
+#define SQ_OK 0
+#define SQ_ERR_INVALID (-1)     /* bad argument / unsupported combination        */
+#define SQ_ERR_CUDA (-2)        /* CUDA runtime error (see sq_last_cuda_error)   */
+#define SQ_ERR_NOMEM (-3)
+#define SQ_ERR_UNSUPPORTED (-4) /* e.g. potential ids 1,2: no kernel in reference */
+#define SQ_ERR_NODEVICE (-5)
+#define SQ_ERR_TIMEOUT (-6)     /* bounded device-side wait expired (halo flags)  */
+
+/* which kernel family */
+enum {
+    /* reference-faithful 1-D kernel: fp64, potID 0|3, ghost-cell boundary, omega
+     * random walk, stability heuristic, per-site running means -- every row of
+     * SURVEY.md 8(a).  One CTA, state on chip for the whole frame. */
+    SQ_KERNEL_COMPAT1D = 0,
+    /* d-dimensional periodic lattice generalisation of SURVEY.md 8(d)
+     * (no reference code): fp32/fp64, potID 0 (W=2) or 4 (phi^4). */
+    SQ_KERNEL_LATTICE = 1
+};
+enum { SQ_REAL_F32 = 0, SQ_REAL_F64 = 1 };
+/* transcendental flavour of the Box-Muller step (tau_kernel.cl:277).  The
+ * integer stream (t1,t2,seed) is bit-exact in both; ACCURATE uses CUDA's
+ * <=2-ulp cosf/logf/sqrtf with the reference's float/double casts, FAST uses
+ * the SFU (MUFU) approximations: |dr| <~ 2e-6 on the N(0,1) draw. */
+enum { SQ_MATH_ACCURATE = 0, SQ_MATH_FAST = 1 };
+
+#define SQ_POT_HARMONIC 0   /* tau_kernel.cl:201-212 */
+#define SQ_POT_DOUBLEWELL 3 /* tau_kernel.cl:184-200 (COMPAT1D only) */
+#define SQ_POT_PHI4 4       /* F = m2*phi + lambda*phi^3 (LATTICE only, not in reference) */
+
+typedef struct sq_ctx sq_ctx;
+
+/* Replaces the argv-derived constants uploaded at tauhost.c:361-377 */
+typedef struct sq_params {
+    uint32_t struct_size; /* = sizeof(sq_params) */
+    int32_t kernel;       /* SQ_KERNEL_*                                          */
+    int32_t real;         /* SQ_REAL_* (COMPAT1D: must be F64)                    */
+    int32_t math;         /* SQ_MATH_*                                            */
+    int32_t potential;    /* `potential` kernel arg, tau_kernel.cl:41             */
+    int32_t ndim;         /* 1..4 (COMPAT1D: 1)                                   */
+    int64_t dims[4];      /* dims[0] fastest; dims[ndim-1] = Euclidean time.
+                             COMPAT1D: dims[0] = LIST_SIZE (tau_kernel.cl:38)     */
+    double spacing;       /* `deltaT`, tau_kernel.cl:39                           */
+    double noise_c;       /* `C`, tau_kernel.cl:42                                */
+    double m2, lambda;    /* SQ_POT_PHI4 only                                     */
+    int32_t device;       /* CUDA ordinal; tauhost maps argv[7] (an OpenCL platform
+                             index, tauhost.c:205) with dev % deviceCount         */
+    int32_t nchains;      /* LATTICE: independent chains in one context (>=1),
+                             chain k starts from seed+k unless sq_set_chain is used */
+    /* slab decomposition along the time axis (LATTICE): this context owns global
+     * time slices [slab_t0, slab_t0+slab_nt).  0,0 = the whole lattice.          */
+    int64_t slab_t0, slab_nt;
+    int32_t steps_per_launch; /* LATTICE: tau-steps fused per launch (0 = auto)   */
+    int32_t flags;            /* SQ_FLAG_*                                        */
+} sq_params;
+
+#define SQ_FLAG_NO_OBSERVABLES 1 /* LATTICE: skip the per-step reductions          */
+#define SQ_FLAG_FORCE_STREAMING 2 /* LATTICE: never use the on-chip resident kernel */
+
+/* What sq_measure copies out.  Pointer members are caller-allocated (or NULL to
+ * skip).  Replaces the per-frame blocking reads tauhost.c:504-515. */
+typedef struct sq_obs {
+    uint32_t struct_size;
+    /* COMPAT1D: committed f, x, xx0 -- N doubles each (tauhost.c:508-513)        */
+    double *f, *x, *xx0;
+    double omega;     /* tauhost.c:514 */
+    uint64_t seed;    /* device RNG seed `rand1` (never read back by the reference) */
+    int32_t lrgEl;    /* tau_kernel.cl:35 */
+    int32_t stable;   /* result of the last sq_step */
+    double lrgVl;     /* tau_kernel.cl:36 */
+    int64_t runs;     /* tau-steps accumulated into the running means             */
+    /* reductions of the current configuration (COMPAT1D: of the path f+cl)       */
+    double mean_phi, mean_phi2;
+    /* LATTICE: per-time-slice running means (Lt doubles each, chain 0, this slab's
+     * slices) of Phi(t) and Phi(t)Phi(t_mid); corr[t] = xx0[t]-x[t]*x[t_mid]
+     * (the host's xavg, tauhost.c:519-521)                                       */
+    double *slice_x, *slice_xx0, *corr;
+    int64_t nclamped; /* sites that hit the +-1000 clamp (tau_kernel.cl:122-132)  */
+    uint64_t nevents; /* RNG chain events replayed (inf-retry / `seed+=`)         */
+    int64_t steps_done; /* tau-steps executed by the last sq_step                 */
+} sq_obs;
+
+/* ---- the four entry points named by BASELINE.json ---------------------------- */
+
+/* Replaces tauhost.c:196-435 (platform/device/context/queue, 19 buffers, 19 uploads,
+ * JIT build, 19 clSetKernelArg).  f0/x0/xx0_0: initial state, N (=volume) doubles
+ * each or NULL for zeros (LATTICE ignores x0/xx0_0; use sq_upload_field for native
+ * fp32 data).  omega0: tauhost.c:84-89.  seed: `rand1`, tauhost.c:185. */
+int sq_init(sq_ctx **out, const sq_params *p, const double *f0, const double *x0,
+            const double *xx0_0, double omega0, uint64_t seed);
+
+/* One reference frame: replaces clEnqueueNDRangeKernel+clFinish (tauhost.c:481-483),
+ * the `stable` read (:504), and the commit / rollback of :506-554.  Runs `nsteps`
+ * (= `Loops`) tau-steps at step size dtau with the running means' counter starting
+ * at runs0 (`runs`, tauhost.c:554).  *stable=1: state committed.  *stable=0
+ * (COMPAT1D): the frame is rolled back to the pre-frame f/x/xx0/omega while RNG
+ * seed, lrgEl, lrgVl keep their new values -- exactly what the reference host
+ * does by not reading back.  Synchronous. */
+int sq_step(sq_ctx *ctx, double dtau, int nsteps, int64_t runs0, int *stable);
+
+/* Replaces the blocking read-backs tauhost.c:508-515 (+ reductions). */
+int sq_measure(sq_ctx *ctx, sq_obs *out);
+
+/* Replaces tauhost.c:587-612. */
+void sq_free(sq_ctx *ctx);
+
+/* ---- support ----------------------------------------------------------------- */
+const char *sq_strerror(int code);
+const char *sq_last_cuda_error(void); /* text of the last CUDA failure, this thread */
+int sq_api_version(void);
+int sq_device_count(void); /* <0 on error, 0 if none */
+
+/* Asynchronous flavour of sq_step for callers that time on the device: enqueues
+ * the launches on the context's stream and returns.  sq_sync finishes the frame
+ * (event replay, commit) and reports stable. */
+int sq_step_async(sq_ctx *ctx, double dtau, int nsteps, int64_t runs0);
+int sq_sync(sq_ctx *ctx, int *stable);
+void *sq_stream(sq_ctx *ctx); /* the cudaStream_t the kernels are launched on */
+int64_t sq_launch_count(sq_ctx *ctx); /* kernels launched by this context so far */
+
+/* Per-launch device timing of the dominant (update) kernel: when enabled, every update-kernel
+ * launch is bracketed by CUDA events on the context's stream; sq_kernel_time returns the summed
+ * elapsed milliseconds and the number of launches since it was enabled.  Off by default (the
+ * event records sit between launches). */
+int sq_kernel_timing(sq_ctx *ctx, int enable);
+int sq_kernel_time(sq_ctx *ctx, double *ms_total, int64_t *launches);
+
+/* LATTICE field transfer in the native or another real type (SQ_REAL_*).
+ * chain: which chain of the batch.  Layout: lexicographic, dims[0] fastest, this
+ * slab's slices only. */
+int sq_upload_field(sq_ctx *ctx, int chain, const void *host, int real);
+int sq_download_field(sq_ctx *ctx, int chain, void *host, int real);
+/* per-chain seed and phi^4 couplings for batched ensembles */
+int sq_set_chain(sq_ctx *ctx, int chain, uint64_t seed, double m2, double lambda);
+/* per-chain observables of a batch: [nchains] each (NULL to skip) */
+int sq_measure_chains(sq_ctx *ctx, double *mean_phi, double *mean_phi2, uint64_t *seeds);
+
+/* End-to-end frame through host buffers (the reference's per-frame traffic,
+ * tauhost.c:550-554 uploads + :508-515 read-backs): H2D of `host_in` (volume reals),
+ * nsteps tau-steps, D2H of the field into `host_out` and of the observables. */
+int sq_frame_host(sq_ctx *ctx, const void *host_in, void *host_out, int real, double dtau,
+                  int nsteps, int64_t runs0, sq_obs *obs, int *stable);
+
+/* Debug / parity hook: the (t1,t2) 48-bit LCG outputs every site of the *next*
+ * tau-step would use (tau_kernel.cl:273,275), computed on the device with the
+ * same jump-ahead code path as the update kernels.  n = number of sites from gid0. */
+int sq_debug_draws(sq_ctx *ctx, int chain, uint64_t gid0, uint64_t n, uint64_t *t1, uint64_t *t2);
+
+/* Host-side utility (no GPU needed): seed before the draw at gid0+ndraws given the seed
+ * before the draw at gid0, assuming no retry / `seed+=` event in between (low 48 bits).
+ * Lets a caller position the shared chain (tau_kernel.cl:269-284) for a slab or a resume. */
+uint64_t sq_lcg_jump(uint64_t seed, uint64_t gid0, uint64_t ndraws);
+
+/* ---- multi-GPU slabs (one process per GPU; handles are exchanged by the caller,
+ * e.g. with torch.distributed) -------------------------------------------------- */
+#define SQ_IPC_HANDLE_BYTES 256
+int sq_slab_export(sq_ctx *ctx, void *handle /* SQ_IPC_HANDLE_BYTES */);
+/* lower/upper: handles of the ranks owning the slabs below/above in time
+ * (periodic).  Pass this context's own handle for a 1-rank ring. */
+int sq_slab_attach(sq_ctx *ctx, const void *lower, const void *upper);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQ_H */

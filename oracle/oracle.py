@@ -91,8 +91,20 @@ def lib() -> C.CDLL:
         L.sqo_read_startfile.restype = C.c_int
         L.sqo_read_startfile.argtypes = [C.c_char_p, C.c_int, C.c_double] + [C.POINTER(C.c_double)] * 4 + [
             C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.sqo_print_frame_path.restype = C.c_int
+        L.sqo_print_frame_path.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_double), C.c_double, C.c_int, C.c_int]
+        L.sqo_tauhost_main_path.restype = C.c_int
+        L.sqo_tauhost_main_path.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_char_p, C.c_int, C.c_int]
         _lib = L
     return _lib
+
+
+def tauhost_main(args, outpath, rng=RNG_CHAIN, field=FIELD_JACOBI) -> int:
+    """The whole reference program on the CPU (tauhost.c:29-621 over the oracle kernel).
+    args: the 13 positional arguments as strings.  stdout stream goes to outpath."""
+    argv = [b"tauhost.o"] + [str(a).encode() for a in args]
+    arr = (C.c_char_p * len(argv))(*argv)
+    return lib().sqo_tauhost_main_path(len(argv), arr, os.fsencode(outpath), rng, field)
 
 
 def _dp(a: np.ndarray):

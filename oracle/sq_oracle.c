@@ -401,6 +401,24 @@ int sqo_tauhost_main(int argc, char **argv, FILE *out, int rng_mode, int field_m
     return rc;
 }
 
+int sqo_print_frame_path(const char *path, int N, const double *xavg, double dtau, int j, int frames)
+{
+    FILE *fp = fopen(path, "w");
+    if (!fp) return -1;
+    int n = sqo_print_frame(fp, N, xavg, dtau, j, frames);
+    fclose(fp);
+    return n;
+}
+
+int sqo_tauhost_main_path(int argc, char **argv, const char *outpath, int rng_mode, int field_mode)
+{
+    FILE *fp = fopen(outpath, "w");
+    if (!fp) return -1;
+    int rc = sqo_tauhost_main(argc, argv, fp, rng_mode, field_mode);
+    fclose(fp);
+    return rc;
+}
+
 /* ------------------------------------------------ chain jump-ahead (oracle) -- */
 /* Outside retry / += events one draw at gid g maps the seed affinely mod 2^48:
  *   t1 = A(s+g)+B ; t2 = A(t1+g)+B ; s' = t2 - 2^31

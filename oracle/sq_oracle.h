@@ -101,6 +101,9 @@ int sqo_read_startfile(const char *path, int N, double deltatau,
  * out = stdout stream.  Returns exit code. */
 int sqo_tauhost_main(int argc, char **argv, FILE *out, int rng_mode, int field_mode);
 
+int sqo_print_frame_path(const char *path, int N, const double *xavg, double dtau, int j, int frames);
+int sqo_tauhost_main_path(int argc, char **argv, const char *outpath, int rng_mode, int field_mode);
+
 /* ---- d-dimensional generalisation ---------------------- */
 enum { SQO_F32 = 0, SQO_F64 = 1 };
 

@@ -1,0 +1,792 @@
+// sq_api.cu -- the C-ABI of include/sq.h: context, stream and memory ownership, launch
+// sequencing, RNG event replay, commit/rollback.  Host side of what tauhost.c:187-481,
+// :504-554 and :587-612 did through OpenCL.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/sq.h"
+#include "sq_kernels.h"
+
+using namespace sq;
+
+static thread_local char g_cuda_err[512] = "";
+
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            snprintf(g_cuda_err, sizeof g_cuda_err, "%s at %s:%d: %s", #call, __FILE__, __LINE__, \
+                     cudaGetErrorString(e__));                                                 \
+            return SQ_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+static constexpr int MAX_SEQ_STEPS = 32768;  // step field of the event key has 16 bits
+static constexpr int MAX_REBASE = 64;
+
+struct sq_ctx {
+    sq_params p{};
+    cudaStream_t stream = nullptr;
+    JumpEntry *d_jump = nullptr;
+    std::vector<JumpEntry> h_jump;
+    int64_t launches = 0;
+    int64_t runs = 0;
+    int last_stable = 1;
+    int64_t last_steps = 0;
+    uint64_t nevents = 0;
+    void *h_pin = nullptr;  // pinned scratch (4 KB)
+
+    // ---- compat 1-D ----
+    double *c_f = nullptr, *c_x = nullptr, *c_xx0 = nullptr, *c_newf = nullptr, *c_newx = nullptr,
+           *c_newxx0 = nullptr, *c_omega = nullptr, *c_lrgVl = nullptr, *c_red = nullptr;
+    u64 *c_seed = nullptr, *c_nevents = nullptr;
+    int *c_stable = nullptr, *c_lrgEl = nullptr, *c_steps = nullptr;
+
+    // ---- lattice ----
+    void *l_field[2] = {nullptr, nullptr};
+    void *l_ghost[2] = {nullptr, nullptr};  // local halo buffers (slab mode without P2P)
+    u64 *l_seeds[2] = {nullptr, nullptr};
+    u64 *l_event = nullptr;
+    RebaseEntry *l_rebase = nullptr;
+    double *l_partials = nullptr, *l_slice_sum = nullptr, *l_slice_x = nullptr, *l_slice_xx0 = nullptr,
+           *l_sums = nullptr, *l_sums_mean = nullptr, *l_m2 = nullptr, *l_lam = nullptr, *l_redbuf = nullptr;
+    unsigned long long *l_nclamped = nullptr;
+    int cur = 0;
+    int nt = 0, ctas_per_slice = 1;
+    int64_t vslice = 0, V = 0, vlocal = 0;
+    size_t rsz = 4;
+    bool per_chain_coupling = false;
+    // pending sequence
+    bool pending = false;
+    double pend_dtau = 0;
+    int pend_nsteps = 0;  // steps currently enqueued
+    int pend_total = 0;   // steps the caller asked for
+    int64_t pend_runs0 = 0;
+    std::vector<RebaseEntry> entries;  // replay entries valid for the first step of the sequence
+    // optional per-launch timing of the update kernel
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    double timing_ms = 0;
+    int64_t timing_launches = 0;
+};
+
+static int timing_mark(sq_ctx *c) {  // record the next pooled event on the stream
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        c->ev_pool.push_back(e);
+    }
+    CK(cudaEventRecord(c->ev_pool[c->ev_used++], c->stream));
+    return SQ_OK;
+}
+static int timing_collect(sq_ctx *c) {  // after a stream sync: sum (start,stop) pairs
+    for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]));
+        c->timing_ms += ms;
+        c->timing_launches++;
+    }
+    c->ev_used = 0;
+    return SQ_OK;
+}
+
+// ------------------------------------------------------------------- helpers --------------
+static int set_dev(sq_ctx *c) {
+    CK(cudaSetDevice(c->p.device));
+    return SQ_OK;
+}
+
+template <typename T>
+static int dalloc(T **p, size_t n) {
+    CK(cudaMalloc((void **)p, n * sizeof(T)));
+    CK(cudaMemset(*p, 0, n * sizeof(T)));
+    return SQ_OK;
+}
+
+extern "C" const char *sq_strerror(int code) {
+    switch (code) {
+        case SQ_OK: return "ok";
+        case SQ_ERR_INVALID: return "invalid argument";
+        case SQ_ERR_CUDA: return "CUDA error";
+        case SQ_ERR_NOMEM: return "out of memory";
+        case SQ_ERR_UNSUPPORTED: return "unsupported (no kernel for this potential / mode in the reference)";
+        case SQ_ERR_NODEVICE: return "no usable CUDA device (libsq has no CPU fallback)";
+        case SQ_ERR_TIMEOUT: return "device-side wait timed out";
+    }
+    return "unknown error";
+}
+extern "C" const char *sq_last_cuda_error(void) { return g_cuda_err; }
+extern "C" int sq_api_version(void) { return SQ_API_VERSION; }
+extern "C" int sq_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        snprintf(g_cuda_err, sizeof g_cuda_err, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? 0 : -1;
+    }
+    return n;
+}
+extern "C" void *sq_stream(sq_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int64_t sq_launch_count(sq_ctx *c) { return c ? c->launches : 0; }
+
+// intConst(potID), tau_kernel.cl:196-200 / :237-246: an all-float expression widened at the end
+static double host_intconst(int pot) {
+    if (pot != 3) return 0.;
+    const float V0f = (float)2., etaf = (float).8;
+    return (double)(sqrtf((float)3.) * powf((float)2., (float)(-5. / 4.)) * powf(V0f, (float)(-1. / 4.)) /
+                    sqrtf(etaf));
+}
+
+// ------------------------------------------------------------------- init / free ----------
+extern "C" void sq_free(sq_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->p.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void *ptrs[] = {c->d_jump, c->c_f, c->c_x, c->c_xx0, c->c_newf, c->c_newx, c->c_newxx0, c->c_omega,
+                    c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps,
+                    c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
+                    c->l_event, c->l_rebase, c->l_partials, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
+                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int init_compat(sq_ctx *c, const double *f0, const double *x0, const double *xx0_0, double omega0,
+                       uint64_t seed) {
+    const sq_params &p = c->p;
+    if (p.ndim != 1 || p.real != SQ_REAL_F64) return SQ_ERR_INVALID;
+    if (p.potential != SQ_POT_HARMONIC && p.potential != SQ_POT_DOUBLEWELL) return SQ_ERR_UNSUPPORTED;
+    const int64_t N = p.dims[0];
+    if (N < 3 || N > 8191) return SQ_ERR_INVALID;
+    int rc;
+    double **arrs[] = {&c->c_f, &c->c_x, &c->c_xx0, &c->c_newf, &c->c_newx, &c->c_newxx0};
+    for (auto a : arrs)
+        if ((rc = dalloc(a, (size_t)N))) return rc;
+    if ((rc = dalloc(&c->c_omega, 1))) return rc;
+    if ((rc = dalloc(&c->c_lrgVl, 1))) return rc;
+    if ((rc = dalloc(&c->c_red, (size_t)N + 8))) return rc;
+    if ((rc = dalloc(&c->c_seed, 1))) return rc;
+    if ((rc = dalloc(&c->c_nevents, 1))) return rc;
+    if ((rc = dalloc(&c->c_stable, 1))) return rc;
+    if ((rc = dalloc(&c->c_lrgEl, 1))) return rc;
+    if ((rc = dalloc(&c->c_steps, 1))) return rc;
+    const size_t nb = sizeof(double) * (size_t)N;
+    // tauhost.c:177-183 + :319-334: new* start as copies of f/x/xx0
+    if (f0) {
+        CK(cudaMemcpy(c->c_f, f0, nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->c_newf, f0, nb, cudaMemcpyHostToDevice));
+    }
+    if (x0) {
+        CK(cudaMemcpy(c->c_x, x0, nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->c_newx, x0, nb, cudaMemcpyHostToDevice));
+    }
+    if (xx0_0) {
+        CK(cudaMemcpy(c->c_xx0, xx0_0, nb, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->c_newxx0, xx0_0, nb, cudaMemcpyHostToDevice));
+    }
+    const int one = 1;
+    CK(cudaMemcpy(c->c_omega, &omega0, sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->c_seed, &seed, sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->c_stable, &one, sizeof(int), cudaMemcpyHostToDevice));
+    return SQ_OK;
+}
+
+static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
+    sq_params &p = c->p;
+    if (p.ndim < 2 || p.ndim > 4) return SQ_ERR_INVALID;
+    if (p.potential != SQ_POT_HARMONIC && p.potential != SQ_POT_PHI4) return SQ_ERR_UNSUPPORTED;
+    if (p.real != SQ_REAL_F32 && p.real != SQ_REAL_F64) return SQ_ERR_INVALID;
+    if (p.nchains < 1) p.nchains = 1;
+    if (p.nchains > 16383) return SQ_ERR_INVALID;
+    c->rsz = p.real == SQ_REAL_F32 ? 4 : 8;
+    const int vec = (int)(16 / c->rsz);
+    int64_t V = 1;
+    for (int k = 0; k < p.ndim; ++k) {
+        if (p.dims[k] < 2) return SQ_ERR_INVALID;
+        V *= p.dims[k];
+    }
+    if (p.dims[0] % vec != 0) return SQ_ERR_INVALID;  // strips never straddle rows
+    const int64_t Lt = p.dims[p.ndim - 1];
+    c->V = V;
+    c->vslice = V / Lt;
+    if (c->vslice >= (1LL << 31) || V >= (1LL << 34)) return SQ_ERR_INVALID;
+    if (p.slab_nt == 0) {
+        p.slab_t0 = 0;
+        p.slab_nt = Lt;
+    }
+    if (p.slab_t0 < 0 || p.slab_nt < 1 || p.slab_t0 + p.slab_nt > Lt || p.slab_nt > 65535) return SQ_ERR_INVALID;
+    if (p.slab_nt != Lt && p.nchains != 1) return SQ_ERR_INVALID;
+    c->nt = (int)p.slab_nt;
+    c->vlocal = c->vslice * c->nt;
+    const int64_t nstrips = c->vslice / vec;
+    // a few strips per thread amortise the table jump; keep >= ~4 CTAs per SM in flight
+    int64_t cps = (nstrips + 256 * 4 - 1) / (256 * 4);
+    if (cps < 1) cps = 1;
+    c->ctas_per_slice = (int)std::min<int64_t>(cps, 65535);
+
+    const size_t fbytes = (size_t)c->vlocal * c->rsz * (size_t)p.nchains;
+    for (int b = 0; b < 2; ++b) {
+        CK(cudaMalloc(&c->l_field[b], fbytes));
+        CK(cudaMemset(c->l_field[b], 0, fbytes));
+        CK(cudaMalloc(&c->l_ghost[b], (size_t)c->vslice * c->rsz));
+        CK(cudaMemset(c->l_ghost[b], 0, (size_t)c->vslice * c->rsz));
+    }
+    int rc;
+    if ((rc = dalloc(&c->l_seeds[0], (size_t)p.nchains))) return rc;
+    if ((rc = dalloc(&c->l_seeds[1], (size_t)p.nchains))) return rc;
+    if ((rc = dalloc(&c->l_event, 1))) return rc;
+    if ((rc = dalloc(&c->l_rebase, MAX_REBASE))) return rc;
+    const size_t npart = (size_t)p.nchains * c->nt * c->ctas_per_slice * 2;
+    if ((rc = dalloc(&c->l_partials, npart))) return rc;
+    const size_t nsl = (size_t)p.nchains * c->nt;
+    if ((rc = dalloc(&c->l_slice_sum, nsl))) return rc;
+    if ((rc = dalloc(&c->l_slice_x, nsl))) return rc;
+    if ((rc = dalloc(&c->l_slice_xx0, nsl))) return rc;
+    if ((rc = dalloc(&c->l_sums, (size_t)p.nchains * 2))) return rc;
+    if ((rc = dalloc(&c->l_sums_mean, (size_t)p.nchains * 2))) return rc;
+    if ((rc = dalloc(&c->l_m2, (size_t)p.nchains))) return rc;
+    if ((rc = dalloc(&c->l_lam, (size_t)p.nchains))) return rc;
+    if ((rc = dalloc(&c->l_redbuf, 2 * 1024))) return rc;
+    if ((rc = dalloc(&c->l_nclamped, 1))) return rc;
+    std::vector<u64> seeds((size_t)p.nchains);
+    std::vector<double> m2((size_t)p.nchains, p.m2), lam((size_t)p.nchains, p.lambda);
+    for (int k = 0; k < p.nchains; ++k) seeds[k] = seed + (u64)k;
+    CK(cudaMemcpy(c->l_seeds[0], seeds.data(), sizeof(u64) * seeds.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->l_m2, m2.data(), sizeof(double) * m2.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->l_lam, lam.data(), sizeof(double) * lam.size(), cudaMemcpyHostToDevice));
+    const u64 none = NO_EVENT;
+    CK(cudaMemcpy(c->l_event, &none, sizeof(u64), cudaMemcpyHostToDevice));
+    if (f0) {
+        rc = sq_upload_field(c, 0, f0, SQ_REAL_F64);
+        if (rc) return rc;
+    }
+    return SQ_OK;
+}
+
+extern "C" int sq_init(sq_ctx **out, const sq_params *p, const double *f0, const double *x0,
+                       const double *xx0_0, double omega0, uint64_t seed) {
+    if (!out || !p) return SQ_ERR_INVALID;
+    *out = nullptr;
+    if (p->struct_size != sizeof(sq_params)) return SQ_ERR_INVALID;
+    const int ndev = sq_device_count();
+    if (ndev <= 0) return SQ_ERR_NODEVICE;
+    if (p->device < 0 || p->device >= ndev) return SQ_ERR_INVALID;
+    sq_ctx *c = new (std::nothrow) sq_ctx();
+    if (!c) return SQ_ERR_NOMEM;
+    c->p = *p;
+    int rc = SQ_OK;
+    do {
+        if ((rc = set_dev(c))) break;
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            snprintf(g_cuda_err, sizeof g_cuda_err, "cudaStreamCreate: %s", cudaGetErrorString(e));
+            rc = SQ_ERR_CUDA;
+            break;
+        }
+        e = cudaMallocHost(&c->h_pin, 4096);
+        if (e != cudaSuccess) { rc = SQ_ERR_NOMEM; break; }
+        c->h_jump.resize(JUMP_TABLE_ENTRIES);
+        build_jump_table(c->h_jump.data());
+        e = cudaMalloc((void **)&c->d_jump, sizeof(JumpEntry) * JUMP_TABLE_ENTRIES);
+        if (e != cudaSuccess) { rc = SQ_ERR_NOMEM; break; }
+        e = cudaMemcpy(c->d_jump, c->h_jump.data(), sizeof(JumpEntry) * JUMP_TABLE_ENTRIES, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { rc = SQ_ERR_CUDA; break; }
+        if (p->kernel == SQ_KERNEL_COMPAT1D) rc = init_compat(c, f0, x0, xx0_0, omega0, seed);
+        else if (p->kernel == SQ_KERNEL_LATTICE) rc = init_lattice(c, f0, seed);
+        else rc = SQ_ERR_INVALID;
+    } while (0);
+    if (rc != SQ_OK) {
+        sq_free(c);
+        return rc;
+    }
+    *out = c;
+    return SQ_OK;
+}
+
+// ------------------------------------------------------------------- stepping -------------
+static int enqueue_compat(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
+    const sq_params &p = c->p;
+    Compat1DArgs A{};
+    A.N = (int)p.dims[0];
+    A.loops = nsteps;
+    A.potential = p.potential;
+    A.runs = runs0;
+    A.dt = p.spacing;
+    A.dtau = dtau;
+    A.dt2 = (double)((float)p.spacing * (float)p.spacing);
+    A.nscale_site = p.noise_c * (double)sqrtf((float)(2. * dtau / p.spacing));
+    A.nscale_omega = p.noise_c * (double)sqrtf((float)(2. * dtau));
+    A.intconst = host_intconst(p.potential);
+    const JumpEntry e = jump_entry((u64)A.N + 1);
+    A.P = e.a & LCG_MASK;
+    A.Q = (LCG_GAMMA * e.g0 + e.bg1) & LCG_MASK;
+    A.jump = c->d_jump;
+    A.f = c->c_f; A.x = c->c_x; A.xx0 = c->c_xx0;
+    A.newf = c->c_newf; A.newx = c->c_newx; A.newxx0 = c->c_newxx0;
+    A.omega = c->c_omega; A.seed = c->c_seed; A.stable = c->c_stable;
+    A.lrgEl = c->c_lrgEl; A.lrgVl = c->c_lrgVl; A.steps_done = c->c_steps; A.nevents = c->c_nevents;
+    if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+    CK(launch_compat1d(A, c->stream));
+    if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+    c->launches++;
+    return SQ_OK;
+}
+
+static LatticeArgs lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */) {
+    const sq_params &p = c->p;
+    LatticeArgs A{};
+    const int vec = (int)(16 / c->rsz);
+    A.ndim = p.ndim;
+    A.pot = p.potential;
+    A.nt = c->nt;
+    A.wrap_time = (c->nt == p.dims[p.ndim - 1]) ? 1 : 0;
+    A.nchains = p.nchains;
+    A.step_index = k;
+    A.n_rebase = 0;
+    A.strips_per_cta_iter = 256 * c->ctas_per_slice;
+    for (int i = 0; i < 4; ++i) A.dim[i] = i < p.ndim ? p.dims[i] : 1;
+    A.vslice = c->vslice;
+    A.V = c->V;
+    A.slab_t0 = p.slab_t0;
+    A.chain_stride = c->vlocal;
+    const int b = (c->cur + k) & 1;
+    A.in = c->l_field[b];
+    A.out = c->l_field[b ^ 1];
+    A.ghost_lo = c->l_ghost[0];
+    A.ghost_hi = c->l_ghost[1];
+    const double a2f = (double)((float)p.spacing * (float)p.spacing);
+    double ad = 1.;
+    for (int i = 0; i < p.ndim; ++i) ad *= p.spacing;
+    A.c_lap = (1. * dtau) / a2f;
+    A.c_dt = dtau;
+    A.nscale = p.noise_c * (double)sqrtf((float)(2. * dtau / ad));
+    A.m2 = p.m2;
+    A.lam = p.lambda;
+    A.m2_chain = c->l_m2;
+    A.lam_chain = c->l_lam;
+    A.seed_in = c->l_seeds[b];
+    A.seed_out = c->l_seeds[b ^ 1];
+    A.stride_jump = jump_entry((u64)A.strips_per_cta_iter * (u64)vec);
+    A.vol_jump = jump_entry((u64)c->V);
+    A.jump = c->d_jump;
+    A.rebase = c->l_rebase;
+    A.event_key = c->l_event;
+    A.partials = (p.flags & SQ_FLAG_NO_OBSERVABLES) ? nullptr : c->l_partials;
+    A.nclamped = c->l_nclamped;
+    return A;
+}
+
+static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
+    const sq_params &p = c->p;
+    LatticeArgs A = lattice_args(c, dtau, 0);
+    const int Lt = (int)p.dims[p.ndim - 1];
+    const int tmid = Lt / 2;
+    for (int k = 0; k < nsteps; ++k) {
+        const int b = (c->cur + k) & 1;
+        A.step_index = k;
+        A.in = c->l_field[b];
+        A.out = c->l_field[b ^ 1];
+        A.seed_in = c->l_seeds[b];
+        A.seed_out = c->l_seeds[b ^ 1];
+        A.n_rebase = (k == 0) ? (int)c->entries.size() : 0;
+        if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+        CK(launch_lattice_step(A, p.real, p.math, c->ctas_per_slice, c->stream));
+        if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+        c->launches++;
+        if (A.partials) {
+            FinalizeArgs F{};
+            F.nt = c->nt;
+            F.nchains = p.nchains;
+            F.ctas_per_slice = c->ctas_per_slice;
+            F.tmid_local = (tmid >= p.slab_t0 && tmid < p.slab_t0 + c->nt) ? (int)(tmid - p.slab_t0) : -1;
+            F.vslice = c->vslice;
+            F.runs = runs0 + k;
+            F.partials = c->l_partials;
+            F.slice_sum = c->l_slice_sum;
+            F.slice_x = c->l_slice_x;
+            F.slice_xx0 = c->l_slice_xx0;
+            F.sums = c->l_sums;
+            F.sums_mean = c->l_sums_mean;
+            F.history = nullptr;
+            F.event_key = c->l_event;
+            CK(launch_finalize(F, c->stream));
+            c->launches++;
+        }
+    }
+    return SQ_OK;
+}
+
+extern "C" int sq_step_async(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
+    if (!c || nsteps < 0 || !(dtau > 0)) return SQ_ERR_INVALID;
+    if (c->pending) return SQ_ERR_INVALID;
+    int rc = set_dev(c);
+    if (rc) return rc;
+    c->pend_dtau = dtau;
+    c->pend_nsteps = nsteps;
+    c->pend_total = nsteps;
+    c->pend_runs0 = runs0;
+    if (c->p.kernel == SQ_KERNEL_COMPAT1D) {
+        if (nsteps > 0 && (rc = enqueue_compat(c, dtau, nsteps, runs0))) return rc;
+    } else {
+        const int n = std::min(nsteps, MAX_SEQ_STEPS);
+        if ((rc = enqueue_lattice(c, dtau, n, runs0))) return rc;
+        c->pend_nsteps = n;  // the remainder is enqueued by sq_sync
+    }
+    c->pending = true;
+    return SQ_OK;
+}
+
+// seed (full u64) before the draw at gid g of the step whose start seed is S, under `entries`
+static u64 host_seed_before(const sq_ctx *c, const std::vector<RebaseEntry> &entries, int chain, u64 S, u64 g) {
+    u64 bg = 0, bs = S;
+    for (const RebaseEntry &e : entries)
+        if (e.chain == chain && e.gid_start <= g && e.gid_start >= bg) { bg = e.gid_start; bs = e.seed; }
+    if (g == bg) return bs;
+    // the draw at g-1 was event-free: seed = t2(g-1) - 2^31 as a full (wrapping) u64
+    const u64 sp = (g - 1 == bg) ? bs : lcg_seed_at(bs, bg, g - 1 - bg, c->h_jump.data());
+    u64 t1, t2;
+    lcg_draw(sp, g - 1, t1, t2);
+    return lcg_next_seed(t2);
+}
+
+static int sync_lattice(sq_ctx *c, int total_steps) {
+    // total_steps = what the caller asked for; pend_nsteps = what is currently enqueued
+    int done = 0;
+    int64_t runs0 = c->pend_runs0;
+    for (;;) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->timing) { int rt = timing_collect(c); if (rt) return rt; }
+        u64 key;
+        CK(cudaMemcpy(&key, c->l_event, sizeof(u64), cudaMemcpyDeviceToHost));
+        int ok_steps = c->pend_nsteps;
+        if (key != NO_EVENT) ok_steps = (int)(key >> KEY_STEP_SHIFT);
+        // steps [0, ok_steps) of the enqueued sequence are valid
+        if (ok_steps > 0) c->entries.clear();  // entries belonged to the sequence's first step
+        c->cur = (c->cur + ok_steps) & 1;
+        done += ok_steps;
+        runs0 += ok_steps;
+        if (key != NO_EVENT) {
+            const int chain = (int)((key >> KEY_CHAIN_SHIFT) & 0x3FFF);
+            const u64 g = key & ((1ULL << KEY_CHAIN_SHIFT) - 1);
+            u64 S;
+            CK(cudaMemcpy(&S, c->l_seeds[c->cur] + chain, sizeof(u64), cudaMemcpyDeviceToHost));
+            const u64 sfull = host_seed_before(c, c->entries, chain, S, g);
+            const HostDraw h = host_draw_literal(sfull, g);
+            RebaseEntry e{};
+            e.gid_start = g + 1;
+            e.seed = h.seed_after;
+            e.ov_gid = g;
+            e.ov_t1 = h.t1;
+            e.ov_t2 = h.t2;
+            e.chain = chain;
+            if ((int)c->entries.size() >= MAX_REBASE) return SQ_ERR_INVALID;
+            c->entries.push_back(e);
+            c->nevents++;
+            CK(cudaMemcpy(c->l_rebase, c->entries.data(), sizeof(RebaseEntry) * c->entries.size(),
+                          cudaMemcpyHostToDevice));
+            const u64 none = NO_EVENT;
+            CK(cudaMemcpy(c->l_event, &none, sizeof(u64), cudaMemcpyHostToDevice));
+        }
+        const int remaining = total_steps - done;
+        if (remaining <= 0) break;
+        const int n = std::min(remaining, MAX_SEQ_STEPS);
+        int rc = enqueue_lattice(c, c->pend_dtau, n, runs0);
+        if (rc) return rc;
+        c->pend_nsteps = n;
+    }
+    c->entries.clear();
+    c->runs = runs0;
+    c->last_stable = 1;
+    c->last_steps = done;
+    return SQ_OK;
+}
+
+extern "C" int sq_sync(sq_ctx *c, int *stable) {
+    if (!c) return SQ_ERR_INVALID;
+    if (!c->pending) {
+        if (stable) *stable = c->last_stable;
+        return SQ_OK;
+    }
+    int rc = set_dev(c);
+    if (rc) return rc;
+    if (c->p.kernel == SQ_KERNEL_COMPAT1D) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->timing) { int rt = timing_collect(c); if (rt) return rt; }
+        if (c->pend_nsteps > 0) {
+            int st = 1, steps = 0;
+            CK(cudaMemcpy(&st, c->c_stable, sizeof(int), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(&steps, c->c_steps, sizeof(int), cudaMemcpyDeviceToHost));
+            c->last_stable = st;
+            c->last_steps = steps;
+            if (st == 1) {
+                c->runs = c->pend_runs0 + c->pend_nsteps;
+            } else {
+                const int one = 1;  // tauhost.c:542-544: the host re-arms the flag
+                CK(cudaMemcpy(c->c_stable, &one, sizeof(int), cudaMemcpyHostToDevice));
+            }
+        }
+    } else {
+        rc = sync_lattice(c, c->pend_total);
+        if (rc) { c->pending = false; return rc; }
+    }
+    c->pending = false;
+    if (stable) *stable = c->last_stable;
+    return SQ_OK;
+}
+
+extern "C" int sq_step(sq_ctx *c, double dtau, int nsteps, int64_t runs0, int *stable) {
+    int rc = sq_step_async(c, dtau, nsteps, runs0);
+    if (rc) return rc;
+    return sq_sync(c, stable);
+}
+
+// ------------------------------------------------------------------- measurement ----------
+extern "C" int sq_measure(sq_ctx *c, sq_obs *o) {
+    if (!c || !o || o->struct_size != sizeof(sq_obs)) return SQ_ERR_INVALID;
+    if (c->pending) return SQ_ERR_INVALID;
+    int rc = set_dev(c);
+    if (rc) return rc;
+    const sq_params &p = c->p;
+    o->runs = c->runs;
+    o->stable = c->last_stable;
+    o->steps_done = c->last_steps;
+    if (p.kernel == SQ_KERNEL_COMPAT1D) {
+        const int N = (int)p.dims[0];
+        const size_t nb = sizeof(double) * (size_t)N;
+        CK(launch_compat_reduce(c->c_f, c->c_x, c->c_xx0, c->c_omega, N, p.spacing, p.potential, c->c_red, c->stream));
+        c->launches++;
+        if (o->f) CK(cudaMemcpyAsync(o->f, c->c_f, nb, cudaMemcpyDeviceToHost, c->stream));
+        if (o->x) CK(cudaMemcpyAsync(o->x, c->c_x, nb, cudaMemcpyDeviceToHost, c->stream));
+        if (o->xx0) CK(cudaMemcpyAsync(o->xx0, c->c_xx0, nb, cudaMemcpyDeviceToHost, c->stream));
+        if (o->corr) CK(cudaMemcpyAsync(o->corr, c->c_red + 8, nb, cudaMemcpyDeviceToHost, c->stream));
+        double *pin = (double *)c->h_pin;
+        CK(cudaMemcpyAsync(pin, c->c_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(pin + 2, c->c_omega, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(pin + 3, c->c_lrgVl, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(pin + 4, c->c_seed, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(pin + 5, c->c_lrgEl, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(pin + 6, c->c_nevents, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        o->mean_phi = pin[0] / N;
+        o->mean_phi2 = pin[1] / N;
+        o->omega = pin[2];
+        o->lrgVl = pin[3];
+        memcpy(&o->seed, pin + 4, sizeof(u64));
+        memcpy(&o->lrgEl, pin + 5, sizeof(int));
+        memcpy(&o->nevents, pin + 6, sizeof(u64));
+        o->nclamped = 0;
+        if (o->slice_x && o->x) memcpy(o->slice_x, o->x, nb);
+        if (o->slice_xx0 && o->xx0) memcpy(o->slice_xx0, o->xx0, nb);
+        return SQ_OK;
+    }
+    // lattice
+    const int nt = c->nt;
+    CK(launch_reduce_field(c->l_field[c->cur], p.real, c->vlocal, p.nchains, c->l_redbuf, c->stream));
+    c->launches++;
+    std::vector<double> part((size_t)REDUCE_BLOCKS * 2), sx((size_t)nt), sxx((size_t)nt);
+    CK(cudaMemcpyAsync(part.data(), c->l_redbuf, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sx.data(), c->l_slice_x, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sxx.data(), c->l_slice_xx0, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long ncl = 0;
+    u64 seed0 = 0;
+    CK(cudaMemcpyAsync(&ncl, c->l_nclamped, sizeof ncl, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&seed0, c->l_seeds[c->cur], sizeof seed0, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    double s1 = 0, s2 = 0;
+    for (int k = 0; k < REDUCE_BLOCKS; ++k) { s1 += part[2 * k]; s2 += part[2 * k + 1]; }
+    o->mean_phi = s1 / (double)c->vlocal;
+    o->mean_phi2 = s2 / (double)c->vlocal;
+    o->seed = seed0;
+    o->nclamped = (int64_t)ncl;
+    o->nevents = c->nevents;
+    o->omega = 0;
+    o->lrgEl = 0;
+    o->lrgVl = 0;
+    if (o->slice_x) memcpy(o->slice_x, sx.data(), sizeof(double) * nt);
+    if (o->slice_xx0) memcpy(o->slice_xx0, sxx.data(), sizeof(double) * nt);
+    if (o->corr) {
+        const int64_t Lt = p.dims[p.ndim - 1];
+        const int64_t tm = Lt / 2 - p.slab_t0;  // the host's xavg, tauhost.c:519-521
+        const double xm = (tm >= 0 && tm < nt) ? sx[(size_t)tm] : 0.;
+        for (int t = 0; t < nt; ++t) o->corr[t] = sxx[t] - sx[t] * xm;
+    }
+    return SQ_OK;
+}
+
+extern "C" int sq_measure_chains(sq_ctx *c, double *mean_phi, double *mean_phi2, uint64_t *seeds) {
+    if (!c || c->p.kernel != SQ_KERNEL_LATTICE || c->pending) return SQ_ERR_INVALID;
+    int rc = set_dev(c);
+    if (rc) return rc;
+    const int nc = c->p.nchains;
+    double *buf = nullptr;
+    CK(cudaMalloc((void **)&buf, sizeof(double) * (size_t)nc * REDUCE_BLOCKS * 2));
+    cudaError_t e = launch_reduce_field(c->l_field[c->cur], c->p.real, c->vlocal, nc, buf, c->stream);
+    c->launches++;
+    std::vector<double> part((size_t)nc * REDUCE_BLOCKS * 2);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(part.data(), buf, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && seeds) e = cudaMemcpyAsync(seeds, c->l_seeds[c->cur], sizeof(u64) * nc, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(buf);
+    CK(e);
+    for (int k = 0; k < nc; ++k) {
+        double s1 = 0, s2 = 0;
+        for (int b = 0; b < REDUCE_BLOCKS; ++b) {
+            s1 += part[((size_t)k * REDUCE_BLOCKS + b) * 2];
+            s2 += part[((size_t)k * REDUCE_BLOCKS + b) * 2 + 1];
+        }
+        if (mean_phi) mean_phi[k] = s1 / (double)c->vlocal;
+        if (mean_phi2) mean_phi2[k] = s2 / (double)c->vlocal;
+    }
+    return SQ_OK;
+}
+
+// ------------------------------------------------------------------- field transfer -------
+static int field_xfer(sq_ctx *c, int chain, void *host, int real, bool upload) {
+    if (!c || !host || c->p.kernel != SQ_KERNEL_LATTICE || c->pending) return SQ_ERR_INVALID;
+    if (chain < 0 || chain >= c->p.nchains || (real != SQ_REAL_F32 && real != SQ_REAL_F64)) return SQ_ERR_INVALID;
+    int rc = set_dev(c);
+    if (rc) return rc;
+    char *dev = (char *)c->l_field[c->cur] + (size_t)chain * c->vlocal * c->rsz;
+    const size_t hsz = real == SQ_REAL_F32 ? 4 : 8;
+    if (real == c->p.real) {
+        if (upload) CK(cudaMemcpyAsync(dev, host, (size_t)c->vlocal * hsz, cudaMemcpyHostToDevice, c->stream));
+        else CK(cudaMemcpyAsync(host, dev, (size_t)c->vlocal * hsz, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return SQ_OK;
+    }
+    void *tmp = nullptr;
+    CK(cudaMalloc(&tmp, (size_t)c->vlocal * hsz));
+    cudaError_t e;
+    if (upload) {
+        e = cudaMemcpyAsync(tmp, host, (size_t)c->vlocal * hsz, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = launch_convert(tmp, real, dev, c->p.real, c->vlocal, c->stream);
+    } else {
+        e = launch_convert(dev, c->p.real, tmp, real, c->vlocal, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host, tmp, (size_t)c->vlocal * hsz, cudaMemcpyDeviceToHost, c->stream);
+    }
+    c->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    CK(e);
+    return SQ_OK;
+}
+extern "C" int sq_upload_field(sq_ctx *c, int chain, const void *host, int real) {
+    return field_xfer(c, chain, const_cast<void *>(host), real, true);
+}
+extern "C" int sq_download_field(sq_ctx *c, int chain, void *host, int real) {
+    return field_xfer(c, chain, host, real, false);
+}
+
+extern "C" int sq_set_chain(sq_ctx *c, int chain, uint64_t seed, double m2, double lambda) {
+    if (!c || c->p.kernel != SQ_KERNEL_LATTICE || c->pending) return SQ_ERR_INVALID;
+    if (chain < 0 || chain >= c->p.nchains) return SQ_ERR_INVALID;
+    int rc = set_dev(c);
+    if (rc) return rc;
+    CK(cudaMemcpy(c->l_seeds[c->cur] + chain, &seed, sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->l_m2 + chain, &m2, sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->l_lam + chain, &lambda, sizeof(double), cudaMemcpyHostToDevice));
+    return SQ_OK;
+}
+
+// ------------------------------------------------------------------- end-to-end frame -----
+extern "C" int sq_frame_host(sq_ctx *c, const void *host_in, void *host_out, int real, double dtau, int nsteps,
+                             int64_t runs0, sq_obs *obs, int *stable) {
+    if (!c || c->pending) return SQ_ERR_INVALID;
+    int rc = set_dev(c);
+    if (rc) return rc;
+    if (c->p.kernel == SQ_KERNEL_COMPAT1D) {
+        if (real != SQ_REAL_F64) return SQ_ERR_INVALID;
+        const size_t nb = sizeof(double) * (size_t)c->p.dims[0];
+        // tauhost.c:550: the host re-uploads f every frame
+        if (host_in) CK(cudaMemcpyAsync(c->c_f, host_in, nb, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = sq_step(c, dtau, nsteps, runs0, stable))) return rc;
+        if (host_out) {
+            CK(cudaMemcpyAsync(host_out, c->c_f, nb, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+    } else {
+        if (real != c->p.real) return SQ_ERR_INVALID;
+        const size_t nb = (size_t)c->vlocal * c->rsz * (size_t)c->p.nchains;
+        if (host_in) CK(cudaMemcpyAsync(c->l_field[c->cur], host_in, nb, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = sq_step(c, dtau, nsteps, runs0, stable))) return rc;
+        if (host_out) {
+            CK(cudaMemcpyAsync(host_out, c->l_field[c->cur], nb, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+    }
+    if (obs) return sq_measure(c, obs);
+    return SQ_OK;
+}
+
+// ------------------------------------------------------------------- parity hook ----------
+extern "C" int sq_debug_draws(sq_ctx *c, int chain, uint64_t gid0, uint64_t n, uint64_t *t1, uint64_t *t2) {
+    if (!c || c->pending || !t1 || !t2) return SQ_ERR_INVALID;
+    int rc = set_dev(c);
+    if (rc) return rc;
+    u64 seed = 0;
+    if (c->p.kernel == SQ_KERNEL_COMPAT1D) {
+        CK(cudaMemcpy(&seed, c->c_seed, sizeof(u64), cudaMemcpyDeviceToHost));
+    } else {
+        if (chain < 0 || chain >= c->p.nchains) return SQ_ERR_INVALID;
+        CK(cudaMemcpy(&seed, c->l_seeds[c->cur] + chain, sizeof(u64), cudaMemcpyDeviceToHost));
+    }
+    u64 *d1 = nullptr, *d2 = nullptr;
+    CK(cudaMalloc((void **)&d1, sizeof(u64) * n));
+    cudaError_t e = cudaMalloc((void **)&d2, sizeof(u64) * n);
+    if (e == cudaSuccess) e = launch_debug_draws(seed, gid0, n, c->d_jump, d1, d2, c->stream);
+    c->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t1, d1, sizeof(u64) * n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t2, d2, sizeof(u64) * n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d1);
+    if (d2) cudaFree(d2);
+    CK(e);
+    return SQ_OK;
+}
+
+extern "C" int sq_kernel_timing(sq_ctx *c, int enable) {
+    if (!c || c->pending) return SQ_ERR_INVALID;
+    c->timing = enable != 0;
+    c->timing_ms = 0;
+    c->timing_launches = 0;
+    c->ev_used = 0;
+    return SQ_OK;
+}
+extern "C" int sq_kernel_time(sq_ctx *c, double *ms_total, int64_t *launches) {
+    if (!c) return SQ_ERR_INVALID;
+    if (ms_total) *ms_total = c->timing_ms;
+    if (launches) *launches = c->timing_launches;
+    return SQ_OK;
+}
+
+extern "C" uint64_t sq_lcg_jump(uint64_t seed, uint64_t gid0, uint64_t ndraws) {
+    static std::vector<JumpEntry> tab;
+    static bool built = false;
+    if (!built) {
+        tab.resize(JUMP_TABLE_ENTRIES);
+        build_jump_table(tab.data());
+        built = true;
+    }
+    return lcg_seed_at(seed, gid0, ndraws, tab.data());
+}
+
+// ------------------------------------------------------------------- slabs (stub stage) ---
+extern "C" int sq_slab_export(sq_ctx *c, void *handle) {
+    if (!c || !handle) return SQ_ERR_INVALID;
+    return SQ_ERR_UNSUPPORTED;
+}
+extern "C" int sq_slab_attach(sq_ctx *c, const void *lower, const void *upper) {
+    if (!c || !lower || !upper) return SQ_ERR_INVALID;
+    return SQ_ERR_UNSUPPORTED;
+}

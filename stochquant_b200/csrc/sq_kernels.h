@@ -1,0 +1,112 @@
+// sq_kernels.h -- argument blocks and launchers shared by the kernels and sq_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sq_lcg.cuh"
+
+namespace sq {
+
+constexpr u64 NO_EVENT = ~0ULL;
+// event key = step_in_sequence (16 bits) | chain (14 bits) | gid (34 bits); the minimum over
+// all detections of a launch sequence is the first genuine event (everything before it was
+// drawn from correct seeds).
+constexpr int KEY_STEP_SHIFT = 48, KEY_CHAIN_SHIFT = 34;
+__host__ __device__ inline u64 event_key(int step, int chain, u64 gid) {
+    return ((u64)step << KEY_STEP_SHIFT) | ((u64)chain << KEY_CHAIN_SHIFT) | gid;
+}
+
+// ---------------------------------------------------------------- compat 1-D ----
+struct Compat1DArgs {
+    int N, loops, potential;
+    long long runs;
+    double dt, dtau;
+    double dt2;           // (double)pown((float)deltat,2), tau_kernel.cl:114
+    double nscale_site;   // c*(double)sqrt((float)(2.*deltatau/deltat)), :112
+    double nscale_omega;  // c*(double)sqrt((float)(2.*deltatau)), :105
+    double intconst;      // intConst(potID), :237-246 (float expression, host-evaluated)
+    u64 P, Q;             // whole-step affine seed advance over N+1 draws
+    const JumpEntry *jump;
+    // device state: the reference's buffers (committed f/x/xx0/omega + persistent new*)
+    double *f, *x, *xx0, *newf, *newx, *newxx0, *omega;
+    u64 *seed;
+    int *stable, *lrgEl, *steps_done;
+    double *lrgVl;
+    u64 *nevents;
+};
+cudaError_t launch_compat1d(const Compat1DArgs &A, cudaStream_t stream);
+
+// ---------------------------------------------------------------- lattice --------
+// one replayed RNG event of the current step (host-resolved, see sq_api.cu)
+struct RebaseEntry {
+    u64 gid_start;  // draws at gid >= gid_start chain from `seed`
+    u64 seed;       // full-u64 seed before the draw at gid_start
+    u64 ov_gid;     // site whose (t1,t2) are overridden (the event site), or NO_EVENT
+    u64 ov_t1, ov_t2;
+    int chain;
+    int pad;
+};
+
+struct LatticeArgs {
+    int ndim;            // 2..4
+    int pot;             // 0 | 4
+    int nt;              // local time slices
+    int wrap_time;       // 1: this context owns the whole time extent (periodic wrap)
+    int nchains;
+    int step_index;      // position in the current launch sequence (event key)
+    int n_rebase;        // entries valid for this step
+    int strips_per_cta_iter;  // blockDim.x * gridDim.x
+    long long dim[4];    // extents, dim[ndim-1] = global Lt
+    long long vslice;    // sites per time slice
+    long long V;         // global volume (= draws per step - 1)
+    long long slab_t0;   // first global slice owned
+    long long chain_stride;  // reals between chains (local volume)
+    const void *in;      // [nchains][nt*vslice]
+    void *out;
+    const void *ghost_lo, *ghost_hi;  // [vslice] slices below / above (slab mode), else unused
+    double c_lap, c_dt, nscale;       // m*dtau/a2f ; dtau ; C*sqrtf(2 dtau/a^d)
+    double m2, lam;                   // used when m2_chain == nullptr
+    const double *m2_chain, *lam_chain;
+    const u64 *seed_in;  // [nchains] full-u64 seed at step start
+    u64 *seed_out;       // [nchains] seed after the step's V+1 draws
+    JumpEntry stride_jump;   // jump over strips_per_cta_iter*VEC draws
+    JumpEntry vol_jump;      // jump over V draws from gid 0 (to the omega draw)
+    const JumpEntry *jump;
+    const RebaseEntry *rebase;
+    u64 *event_key;      // atomicMin target; != NO_EVENT also aborts later launches
+    double *partials;    // [nchains][nt][ctas_per_slice][2] (sum phi, sum phi^2), or null
+    unsigned long long *nclamped;
+};
+cudaError_t launch_lattice_step(const LatticeArgs &A, int real, int math, int ctas_per_slice,
+                                cudaStream_t stream);
+
+struct FinalizeArgs {
+    int nt, nchains, ctas_per_slice;
+    int tmid_local;      // local index of the global mid slice, or -1 if not owned
+    long long vslice;
+    long long runs;      // running-mean counter before this step
+    const double *partials;
+    double *slice_sum;   // [nchains][nt]   last step's slice sums
+    double *slice_x;     // [nchains][nt]   running mean of Phi(t)
+    double *slice_xx0;   // [nchains][nt]   running mean of Phi(t) Phi(t_mid)
+    double *sums;        // [nchains][2]    last step's global sums (phi, phi^2)
+    double *sums_mean;   // [nchains][2]    running means of <phi>, <phi^2>
+    double *history;     // slab mode: [nt] slice sums of this step appended, else null
+    const u64 *event_key;
+};
+cudaError_t launch_finalize(const FinalizeArgs &A, cudaStream_t stream);
+
+cudaError_t launch_debug_draws(u64 seed, u64 gid0, u64 n, const JumpEntry *jump, u64 *t1, u64 *t2,
+                               cudaStream_t stream);
+// current-configuration reductions: partial sums [nchains][nblocks][2] (phi, phi^2), fixed order
+constexpr int REDUCE_BLOCKS = 256;
+cudaError_t launch_reduce_field(const void *field, int real, long long nper_chain, int nchains,
+                                double *partials, cudaStream_t stream);
+// compat 1-D: sums of the path f+cl and its square, and corr[i] = xx0[i]-x[i]*x[mid]
+// out: [0]=sum path, [1]=sum path^2, [8..8+N) = corr
+cudaError_t launch_compat_reduce(const double *f, const double *x, const double *xx0, const double *omega,
+                                 int N, double dt, int pot, double *out, cudaStream_t stream);
+cudaError_t launch_convert(const void *src, int src_real, void *dst, int dst_real, long long n,
+                           cudaStream_t stream);
+
+}  // namespace sq

@@ -1,0 +1,381 @@
+// sq_lattice.cu -- streaming Langevin step for d-dimensional periodic lattices (d = 2..4).
+//
+// Generalises the fused body of time_dev (/root/reference/tau_kernel.cl:64-173: noise ->
+// stencil drift -> Euler update -> clamp -> observables) to the lattices of SURVEY.md 8(d):
+//   phi' = phi + (dtau/a2f) (sum_nn phi - 2d phi) - dtau F(phi) + C sqrt(2 dtau/a^d) r(gid)
+// with gid = lexicographic site index (dims[0] fastest, last dim = Euclidean time) and
+// r(gid) drawn from the reference's shared-seed LCG chain in gid order (sq_lcg.cuh), one
+// extra draw at gid = V per step standing for the omega work-item (:103-110).
+//
+// Data layout / mapping (HBM-bound, no tensor cores):
+//   * field: [chain][t][x_{d-2}]..[x_0] contiguous, fp32 or fp64, ping-pong buffers;
+//   * one CTA works inside ONE time slice (grid.y = slice, grid.z = chain) so that its
+//     observable partial is a single slice sum; each thread owns 16-byte strips of
+//     consecutive x_0 sites: 128-bit coalesced loads/stores, RNG chained inside the strip;
+//   * the seed at a strip start comes from affine jump-ahead (first strip: table jump,
+//     later strips of the grid-stride loop: one fixed-stride jump);
+//   * per-slice sum(phi), sum(phi^2): registers -> warp shuffle -> one fp64 partial per
+//     CTA, reduced in fixed order by finalize_kernel (bit-reproducible, no float atomics).
+#include "sq_kernels.h"
+#include "sq_noise.cuh"
+
+namespace sq {
+
+namespace {
+
+template <typename real>
+struct alignas(16) Pack {
+    real v[16 / sizeof(real)];
+};
+
+template <typename real> struct Ops;
+template <> struct Ops<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+};
+template <> struct Ops<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// base (gid, seed) applicable to draws starting at gid g under the step's rebase list
+__device__ __forceinline__ void rebase_lookup(const LatticeArgs &A, int chain, u64 S, u64 g,
+                                              u64 &bg, u64 &bs) {
+    bg = 0;
+    bs = S;
+    for (int j = 0; j < A.n_rebase; ++j) {
+        const RebaseEntry e = A.rebase[j];
+        if (e.chain == chain && e.gid_start <= g && e.gid_start >= bg) {
+            bg = e.gid_start;
+            bs = e.seed;
+        }
+    }
+}
+
+}  // namespace
+
+template <typename real, int MATH, int NDIM, bool REBASE>
+__global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) {
+    using O = Ops<real>;
+    constexpr int VEC = 16 / sizeof(real);
+    if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;  // an earlier launch must be replayed
+
+    const int chain = blockIdx.z, tl = blockIdx.y;
+    const long long vs = A.vslice;
+    const real *in = (const real *)A.in + (long long)chain * A.chain_stride;
+    real *out = (real *)A.out + (long long)chain * A.chain_stride;
+    const real *cur = in + (long long)tl * vs;
+    const real *tm = (tl > 0) ? cur - vs : (A.wrap_time ? in + (long long)(A.nt - 1) * vs : (const real *)A.ghost_lo);
+    const real *tp = (tl < A.nt - 1) ? cur + vs : (A.wrap_time ? in : (const real *)A.ghost_hi);
+    real *dst = out + (long long)tl * vs;
+
+    const u64 gslice = (u64)(A.slab_t0 + tl) * (u64)vs;
+    const u64 S = A.seed_in[chain];
+    const real c_lap = (real)A.c_lap, c_dt = (real)A.c_dt;
+    const real m2 = (real)(A.m2_chain ? A.m2_chain[chain] : A.m2);
+    const real lam = (real)(A.lam_chain ? A.lam_chain[chain] : A.lam);
+    const float nscale_f = (float)A.nscale;
+    const unsigned L0 = (unsigned)A.dim[0];
+    const unsigned L1 = (NDIM >= 3) ? (unsigned)A.dim[1] : 1u;
+    const unsigned L2 = (NDIM >= 4) ? (unsigned)A.dim[2] : 1u;
+    const unsigned nstrips = (unsigned)(vs / VEC);
+
+    real acc1 = 0, acc2 = 0;
+    unsigned nclamp = 0;
+    u64 s_prev = 0, g_prev = 0;
+    bool first = true;
+
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < nstrips; q += (unsigned)A.strips_per_cta_iter) {
+        const unsigned off = q * VEC;
+        const u64 g0 = gslice + off;
+        // ---- seed before the draw at g0 ---------------------------------------------
+        u64 s;
+        if (REBASE) {
+            u64 bg, bs;
+            rebase_lookup(A, chain, S, g0, bg, bs);
+            s = lcg_seed_at(bs, bg, g0 - bg, A.jump);
+        } else if (first) {
+            s = lcg_seed_at(S, 0, g0, A.jump);
+        } else {
+            s = lcg_apply(A.stride_jump, s_prev, g_prev) & LCG_MASK;
+        }
+        first = false;
+        s_prev = s;
+        g_prev = g0;
+
+        // ---- loads -----------------------------------------------------------------------
+        const unsigned x0 = off % L0;
+        const unsigned rest = off / L0;
+        const Pack<real> c = *reinterpret_cast<const Pack<real> *>(cur + off);
+        const Pack<real> pm = *reinterpret_cast<const Pack<real> *>(tm + off);
+        const Pack<real> pp = *reinterpret_cast<const Pack<real> *>(tp + off);
+        Pack<real> u1, d1, u2, d2;
+        if (NDIM >= 3) {
+            const unsigned x1 = (NDIM >= 4) ? rest % L1 : rest;
+            const long long up = (x1 + 1 == L1) ? -(long long)(L1 - 1) * L0 : (long long)L0;
+            const long long dn = (x1 == 0) ? (long long)(L1 - 1) * L0 : -(long long)L0;
+            u1 = *reinterpret_cast<const Pack<real> *>(cur + off + up);
+            d1 = *reinterpret_cast<const Pack<real> *>(cur + off + dn);
+        }
+        if (NDIM >= 4) {
+            const unsigned x2 = rest / L1;
+            const long long st2 = (long long)L0 * L1;
+            const long long up = (x2 + 1 == L2) ? -(long long)(L2 - 1) * st2 : st2;
+            const long long dn = (x2 == 0) ? (long long)(L2 - 1) * st2 : -st2;
+            u2 = *reinterpret_cast<const Pack<real> *>(cur + off + up);
+            d2 = *reinterpret_cast<const Pack<real> *>(cur + off + dn);
+        }
+        const real left = cur[(x0 == 0) ? off + L0 - 1 : off - 1];
+        const real right = cur[(x0 + VEC == L0) ? off + VEC - L0 : off + VEC];
+
+        // ---- per-site: draw, update ------------------------------------------------------
+        Pack<real> res;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const u64 g = g0 + e;
+            u64 t1, t2;
+            bool overridden = false;
+            if (REBASE) {
+                for (int j = 0; j < A.n_rebase; ++j)
+                    if (A.rebase[j].chain == chain && A.rebase[j].gid_start == g) s = A.rebase[j].seed;
+            }
+            lcg_draw(s, g, t1, t2);
+            if (REBASE) {
+                for (int j = 0; j < A.n_rebase; ++j)
+                    if (A.rebase[j].chain == chain && A.rebase[j].ov_gid == g) {
+                        t1 = A.rebase[j].ov_t1;
+                        t2 = A.rebase[j].ov_t2;
+                        overridden = true;
+                    }
+            }
+            if (!overridden && lcg_event(s & LCG_MASK, t1, t2))
+                atomicMin((unsigned long long *)A.event_key, event_key(A.step_index, chain, g));
+            s = lcg_next_seed(t2) & LCG_MASK;
+
+            real dw;
+            if (MATH == 1) {
+                const float r = noise_fast(t1, t2);
+                if (sizeof(real) == 4) dw = (real)__fmul_rn(nscale_f, r);
+                else dw = (real)__dmul_rn(A.nscale, (double)r);
+            } else {
+                dw = (real)__dmul_rn(A.nscale, noise_accurate(t1, t2));
+            }
+            const real phi = c.v[e];
+            const real nbp = (e < VEC - 1) ? c.v[(e + 1) % VEC] : right;
+            const real nbm = (e > 0) ? c.v[(e + VEC - 1) % VEC] : left;
+            real sum = O::add(nbp, nbm);
+            if (NDIM >= 3) {
+                sum = O::add(sum, u1.v[e]);
+                sum = O::add(sum, d1.v[e]);
+            }
+            if (NDIM >= 4) {
+                sum = O::add(sum, u2.v[e]);
+                sum = O::add(sum, d2.v[e]);
+            }
+            sum = O::add(sum, pp.v[e]);
+            sum = O::add(sum, pm.v[e]);
+            const real lap = O::fma(-(real)(2 * NDIM), phi, sum);
+            real F;
+            if (A.pot == 4) F = O::mul(phi, O::fma(lam, O::mul(phi, phi), m2));
+            else F = O::mul((real)2, phi);
+            real v = O::fma(c_lap, lap, phi);
+            v = O::fma(-c_dt, F, v);
+            v = O::add(v, dw);
+            if (v > (real)1000) { v = (real)1000; ++nclamp; }
+            else if (v < -(real)1000) { v = -(real)1000; ++nclamp; }
+            else if (!(v == v)) { v = (real)1000; ++nclamp; }
+            res.v[e] = v;
+            acc1 = O::add(acc1, phi);
+            acc2 = O::fma(phi, phi, acc2);
+        }
+        *reinterpret_cast<Pack<real> *>(dst + off) = res;
+    }
+
+    // ---- the omega work-item's draw (gid = V) and the step's final seed -----------------
+    if (blockIdx.x == 0 && tl == 0 && threadIdx.x == 0) {
+        const u64 Vg = (u64)A.V;
+        u64 s, t1, t2;
+        bool overridden = false;
+        u64 next = 0;
+        if (REBASE) {
+            u64 bg, bs;
+            rebase_lookup(A, chain, S, Vg, bg, bs);
+            s = lcg_seed_at(bs, bg, Vg - bg, A.jump);
+            for (int j = 0; j < A.n_rebase; ++j)
+                if (A.rebase[j].chain == chain && A.rebase[j].ov_gid == Vg) {
+                    overridden = true;
+                    next = A.rebase[j].seed;  // entry with gid_start == V+1
+                }
+        } else {
+            s = lcg_apply(A.vol_jump, S, 0) & LCG_MASK;
+        }
+        lcg_draw(s, Vg, t1, t2);
+        if (!overridden) {
+            if (lcg_event(s & LCG_MASK, t1, t2))
+                atomicMin((unsigned long long *)A.event_key, event_key(A.step_index, chain, Vg));
+            next = lcg_next_seed(t2);
+        }
+        A.seed_out[chain] = next;
+    }
+
+    // ---- per-CTA observable partial ------------------------------------------------------
+    if (A.partials) {
+        __shared__ double red[2][8];
+        double a1 = warp_sum((double)acc1), a2 = warp_sum((double)acc2);
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0) { red[0][w] = a1; red[1][w] = a2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s1 = 0, s2 = 0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { s1 += red[0][k]; s2 += red[1][k]; }
+            double *p = A.partials + (((long long)chain * A.nt + tl) * gridDim.x + blockIdx.x) * 2;
+            p[0] = s1;
+            p[1] = s2;
+        }
+    }
+    if (nclamp) atomicAdd(A.nclamped, (unsigned long long)nclamp);
+}
+
+// ---- finalize: fixed-order reduction of the partials + Welford running means ------------
+// (tau_kernel.cl:144-145 at time-slice granularity; the host's xavg is derived in sq_measure)
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs A) {
+    extern __shared__ double ssum[];  // [nt] slice sums, then [nt] phi^2 sums
+    if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;
+    const int chain = blockIdx.x;
+    double *s1 = ssum, *s2 = ssum + A.nt;
+    for (int t = threadIdx.x; t < A.nt; t += blockDim.x) {
+        const double *p = A.partials + ((long long)chain * A.nt + t) * A.ctas_per_slice * 2;
+        double a = 0, b = 0;
+        for (int k = 0; k < A.ctas_per_slice; ++k) { a += p[2 * k]; b += p[2 * k + 1]; }
+        s1[t] = a;
+        s2[t] = b;
+        A.slice_sum[(long long)chain * A.nt + t] = a;
+        if (A.history && chain == 0) A.history[t] = a;
+    }
+    __syncthreads();
+    if (A.tmid_local >= 0 && !A.history) {
+        const double n = (double)(A.runs + 1);
+        const double pmid = s1[A.tmid_local] / (double)A.vslice;
+        for (int t = threadIdx.x; t < A.nt; t += blockDim.x) {
+            const long long i = (long long)chain * A.nt + t;
+            const double P = s1[t] / (double)A.vslice;
+            A.slice_xx0[i] = A.slice_xx0[i] + (P * pmid - A.slice_xx0[i]) / n;
+            A.slice_x[i] = A.slice_x[i] + (P - A.slice_x[i]) / n;
+        }
+    }
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0;
+        for (int t = 0; t < A.nt; ++t) { a += s1[t]; b += s2[t]; }
+        A.sums[chain * 2] = a;
+        A.sums[chain * 2 + 1] = b;
+        const double n = (double)(A.runs + 1);
+        const double vol = (double)A.vslice * (double)A.nt;
+        A.sums_mean[chain * 2] += (a / vol - A.sums_mean[chain * 2]) / n;
+        A.sums_mean[chain * 2 + 1] += (b / vol - A.sums_mean[chain * 2 + 1]) / n;
+    }
+}
+
+cudaError_t launch_finalize(const FinalizeArgs &A, cudaStream_t stream) {
+    finalize_kernel<<<A.nchains, 256, sizeof(double) * 2 * (size_t)A.nt, stream>>>(A);
+    return cudaGetLastError();
+}
+
+template <typename real, int MATH, int NDIM>
+static cudaError_t launch_rb(const LatticeArgs &A, dim3 grid, cudaStream_t st) {
+    if (A.n_rebase > 0) lattice_step_kernel<real, MATH, NDIM, true><<<grid, 256, 0, st>>>(A);
+    else lattice_step_kernel<real, MATH, NDIM, false><<<grid, 256, 0, st>>>(A);
+    return cudaGetLastError();
+}
+template <typename real, int MATH>
+static cudaError_t launch_nd(const LatticeArgs &A, dim3 grid, cudaStream_t st) {
+    switch (A.ndim) {
+        case 2: return launch_rb<real, MATH, 2>(A, grid, st);
+        case 3: return launch_rb<real, MATH, 3>(A, grid, st);
+        case 4: return launch_rb<real, MATH, 4>(A, grid, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_lattice_step(const LatticeArgs &A, int real, int math, int ctas_per_slice,
+                                cudaStream_t stream) {
+    dim3 grid((unsigned)ctas_per_slice, (unsigned)A.nt, (unsigned)A.nchains);
+    if (real == 0) return math ? launch_nd<float, 1>(A, grid, stream) : launch_nd<float, 0>(A, grid, stream);
+    return math ? launch_nd<double, 1>(A, grid, stream) : launch_nd<double, 0>(A, grid, stream);
+}
+
+// ---- parity hook: the integer stream as the update kernels derive it --------------------
+__global__ void debug_draws_kernel(u64 seed, u64 gid0, u64 n, const JumpEntry *jump, u64 *t1, u64 *t2) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 g = gid0 + i;
+    const u64 s = lcg_seed_at(seed, 0, g, jump);
+    u64 a, b;
+    lcg_draw(s, g, a, b);
+    t1[i] = a;
+    t2[i] = b;
+}
+cudaError_t launch_debug_draws(u64 seed, u64 gid0, u64 n, const JumpEntry *jump, u64 *t1, u64 *t2,
+                               cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    debug_draws_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(seed, gid0, n, jump, t1, t2);
+    return cudaGetLastError();
+}
+
+// ---- <phi>, <phi^2> of the current configuration: registers -> warp shuffle -> block ----
+template <typename real>
+__global__ void __launch_bounds__(256) reduce_field_kernel(const real *field, long long n, double *partials) {
+    const int chain = blockIdx.y;
+    const real *f = field + (long long)chain * n;
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    const long long b = (long long)blockIdx.x * per, e = (b + per < n) ? b + per : n;
+    double a1 = 0, a2 = 0;
+    for (long long i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const double v = (double)f[i];
+        a1 += v;
+        a2 = fma(v, v, a2);
+    }
+    __shared__ double red[2][8];
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[0][w] = a1; red[1][w] = a2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s1 = 0, s2 = 0;
+        for (int k = 0; k < 8; ++k) { s1 += red[0][k]; s2 += red[1][k]; }
+        partials[((long long)chain * gridDim.x + blockIdx.x) * 2] = s1;
+        partials[((long long)chain * gridDim.x + blockIdx.x) * 2 + 1] = s2;
+    }
+}
+cudaError_t launch_reduce_field(const void *field, int real, long long n, int nchains, double *partials,
+                                cudaStream_t st) {
+    dim3 grid(REDUCE_BLOCKS, (unsigned)nchains);
+    if (real == 0) reduce_field_kernel<float><<<grid, 256, 0, st>>>((const float *)field, n, partials);
+    else reduce_field_kernel<double><<<grid, 256, 0, st>>>((const double *)field, n, partials);
+    return cudaGetLastError();
+}
+
+template <typename S, typename D>
+__global__ void convert_kernel(const S *src, D *dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = (D)src[i];
+}
+cudaError_t launch_convert(const void *src, int sr, void *dst, int dr, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + 255) / 256 > 148 * 16 ? 148 * 16 : (n + 255) / 256);
+    if (sr == 0 && dr == 0) convert_kernel<float, float><<<grid, 256, 0, st>>>((const float *)src, (float *)dst, n);
+    else if (sr == 0 && dr == 1) convert_kernel<float, double><<<grid, 256, 0, st>>>((const float *)src, (double *)dst, n);
+    else if (sr == 1 && dr == 0) convert_kernel<double, float><<<grid, 256, 0, st>>>((const double *)src, (float *)dst, n);
+    else convert_kernel<double, double><<<grid, 256, 0, st>>>((const double *)src, (double *)dst, n);
+    return cudaGetLastError();
+}
+
+}  // namespace sq
