@@ -29,6 +29,8 @@ static thread_local char g_cuda_err[512] = "";
 
 static constexpr int MAX_SEQ_STEPS = 32768;  // step field of the event key has 16 bits
 static constexpr int MAX_REBASE = 64;
+static constexpr int RES_MAX_STEPS = 2048;  // tau-steps per resident launch (history buffer)
+static constexpr int RES_MAX_ROWS = 8;
 
 struct sq_ctx {
     sq_params p{};
@@ -62,6 +64,15 @@ struct sq_ctx {
     int64_t vslice = 0, V = 0, vlocal = 0;
     size_t rsz = 4;
     bool per_chain_coupling = false;
+    // resident 2-D path (sq_resident.cu)
+    bool res_ok = false;
+    int res_nb = 0, res_rows = 0;
+    float *r_halo = nullptr;
+    unsigned *r_flags = nullptr, *r_error = nullptr;
+    double *r_hist_rows = nullptr, *r_hist_p2 = nullptr;
+    int res_limit = 0;      // >0: the next resident batch must stop after this many steps
+    int force_stream = 0;   // >0: this many steps must go through the streaming kernel
+    int pend_kind = 0;      // 0 streaming, 1 resident
     // pending sequence
     bool pending = false;
     double pend_dtau = 0;
@@ -153,7 +164,8 @@ extern "C" void sq_free(sq_ctx *c) {
                     c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps,
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
-                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped};
+                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped,
+                    c->r_halo, c->r_flags, c->r_error, c->r_hist_rows, c->r_hist_p2};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -270,6 +282,29 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
     if (f0) {
         rc = sq_upload_field(c, 0, f0, SQ_REAL_F64);
         if (rc) return rc;
+    }
+    // the on-chip resident kernel: 2-D fp32 single chain, whole lattice, rows of 128..1024 sites
+    {
+        int coop = 0, sms = 0;
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p.device));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p.device));
+        const int64_t L0 = p.dims[0], L1 = p.dims[1];
+        const bool shape_ok = p.ndim == 2 && p.real == SQ_REAL_F32 && p.nchains == 1 && c->nt == Lt &&
+                              L0 % 128 == 0 && L0 <= 1024 && !(p.flags & (SQ_FLAG_FORCE_STREAMING | SQ_FLAG_NO_OBSERVABLES));
+        if (coop && shape_ok && sms > 0) {
+            const int nb = (int)std::min<int64_t>(sms, L1);
+            const int rows = (int)((L1 + nb - 1) / nb);
+            if (rows <= RES_MAX_ROWS) {
+                c->res_ok = true;
+                c->res_nb = nb;
+                c->res_rows = rows;
+                CK(cudaMalloc((void **)&c->r_halo, sizeof(float) * 2 * (size_t)nb * 2 * (size_t)L0));
+                if ((rc = dalloc(&c->r_flags, (size_t)nb))) return rc;
+                if ((rc = dalloc(&c->r_error, 1))) return rc;
+                if ((rc = dalloc(&c->r_hist_rows, (size_t)RES_MAX_STEPS * (size_t)L1))) return rc;
+                if ((rc = dalloc(&c->r_hist_p2, (size_t)RES_MAX_STEPS * (size_t)nb))) return rc;
+            }
+        }
     }
     return SQ_OK;
 }
@@ -427,6 +462,85 @@ static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     return SQ_OK;
 }
 
+static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
+    const sq_params &p = c->p;
+    const LatticeArgs L = lattice_args(c, dtau, 0);
+    ResidentArgs A{};
+    A.L0 = (int)p.dims[0];
+    A.L1 = (int)p.dims[1];
+    A.nsteps = nsteps;
+    A.pot = p.potential;
+    A.step_index0 = 0;
+    A.step0 = 0;
+    A.V = c->V;
+    A.in = (const float *)c->l_field[c->cur];
+    A.out = (float *)c->l_field[c->cur ^ 1];
+    A.halo = c->r_halo;
+    A.flags = c->r_flags;
+    A.c_lap = L.c_lap;
+    A.c_dt = L.c_dt;
+    A.nscale = L.nscale;
+    A.m2 = p.m2;
+    A.lam = p.lambda;
+    A.seed_in = c->l_seeds[c->cur];
+    A.seed_out = c->l_seeds[c->cur ^ 1];
+    const JumpEntry e = jump_entry((u64)c->V + 1);
+    A.P = e.a & LCG_MASK;
+    A.Q = (LCG_GAMMA * e.g0 + e.bg1) & LCG_MASK;
+    A.vol_jump = L.vol_jump;
+    A.jump = c->d_jump;
+    A.event_key = c->l_event;
+    A.hist_rows = c->r_hist_rows;
+    A.hist_p2 = c->r_hist_p2;
+    A.nclamped = c->l_nclamped;
+    A.error_flag = c->r_error;
+    // per-chain couplings live in device arrays for the streaming kernel; the resident kernel is
+    // single-chain and takes them by value: keep both in sync through sq_set_chain (host mirror)
+    CK(cudaMemsetAsync(c->r_flags, 0, sizeof(unsigned) * (size_t)c->res_nb, c->stream));
+    if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+    CK(launch_resident2d(A, p.math, c->res_nb, c->res_rows, c->stream));
+    if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+    c->launches++;
+    WelfordArgs W{};
+    W.nt = c->nt;
+    W.nsteps = nsteps;
+    W.tmid = (int)(p.dims[1] / 2);
+    W.np2 = c->res_nb;
+    W.vslice = c->vslice;
+    W.runs = runs0;
+    W.hist_rows = c->r_hist_rows;
+    W.hist_p2 = c->r_hist_p2;
+    W.slice_x = c->l_slice_x;
+    W.slice_xx0 = c->l_slice_xx0;
+    W.slice_sum = c->l_slice_sum;
+    W.sums = c->l_sums;
+    W.sums_mean = c->l_sums_mean;
+    W.event_key = c->l_event;
+    CK(launch_welford_history(W, c->stream));
+    c->launches++;
+    return SQ_OK;
+}
+
+// enqueue the next batch of the pending sequence; sets pend_kind / pend_nsteps
+static int enqueue_batch(sq_ctx *c, int remaining, int64_t runs0) {
+    if (c->res_ok && c->entries.empty() && c->force_stream == 0) {
+        int n = std::min(remaining, RES_MAX_STEPS);
+        if (c->res_limit > 0) n = std::min(n, c->res_limit);
+        int rc = enqueue_resident(c, c->pend_dtau, n, runs0);
+        if (rc) return rc;
+        c->pend_kind = 1;
+        c->pend_nsteps = n;
+    } else {
+        int n = std::min(remaining, MAX_SEQ_STEPS);
+        if (c->force_stream > 0) n = std::min(n, c->force_stream);
+        int rc = enqueue_lattice(c, c->pend_dtau, n, runs0);
+        if (rc) return rc;
+        c->pend_kind = 0;
+        c->pend_nsteps = n;
+    }
+    return SQ_OK;
+}
+
 extern "C" int sq_step_async(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     if (!c || nsteps < 0 || !(dtau > 0)) return SQ_ERR_INVALID;
     if (c->pending) return SQ_ERR_INVALID;
@@ -438,10 +552,8 @@ extern "C" int sq_step_async(sq_ctx *c, double dtau, int nsteps, int64_t runs0) 
     c->pend_runs0 = runs0;
     if (c->p.kernel == SQ_KERNEL_COMPAT1D) {
         if (nsteps > 0 && (rc = enqueue_compat(c, dtau, nsteps, runs0))) return rc;
-    } else {
-        const int n = std::min(nsteps, MAX_SEQ_STEPS);
-        if ((rc = enqueue_lattice(c, dtau, n, runs0))) return rc;
-        c->pend_nsteps = n;  // the remainder is enqueued by sq_sync
+    } else if (nsteps > 0) {
+        if ((rc = enqueue_batch(c, nsteps, runs0))) return rc;
     }
     c->pending = true;
     return SQ_OK;
@@ -460,52 +572,77 @@ static u64 host_seed_before(const sq_ctx *c, const std::vector<RebaseEntry> &ent
     return lcg_next_seed(t2);
 }
 
-static int sync_lattice(sq_ctx *c, int total_steps) {
-    // total_steps = what the caller asked for; pend_nsteps = what is currently enqueued
+// Finish the pending lattice sequence.  RNG events (inf-retry / `seed+=`, tau_kernel.cl:278-282)
+// are speculated away on the device and replayed here:
+//   streaming batch, event at step k: steps < k stand; the host replays the event draw literally,
+//     appends a rebase entry and the sequence resumes at step k with the entry list;
+//   resident batch (one launch = many steps, output written at the end): nothing stands; the
+//     batch is re-run up to the event step, then ONE streaming step takes the event.
+static int sync_lattice(sq_ctx *c) {
+    const int total = c->pend_total;
     int done = 0;
     int64_t runs0 = c->pend_runs0;
-    for (;;) {
+    while (total > 0) {
         CK(cudaStreamSynchronize(c->stream));
         if (c->timing) { int rt = timing_collect(c); if (rt) return rt; }
         u64 key;
         CK(cudaMemcpy(&key, c->l_event, sizeof(u64), cudaMemcpyDeviceToHost));
-        int ok_steps = c->pend_nsteps;
-        if (key != NO_EVENT) ok_steps = (int)(key >> KEY_STEP_SHIFT);
-        // steps [0, ok_steps) of the enqueued sequence are valid
-        if (ok_steps > 0) c->entries.clear();  // entries belonged to the sequence's first step
-        c->cur = (c->cur + ok_steps) & 1;
-        done += ok_steps;
-        runs0 += ok_steps;
+        const int n = c->pend_nsteps;
+        if (c->pend_kind == 1) {
+            unsigned err = 0;
+            CK(cudaMemcpy(&err, c->r_error, sizeof err, cudaMemcpyDeviceToHost));
+            if (err) return SQ_ERR_TIMEOUT;
+            if (key == NO_EVENT) {
+                c->cur ^= 1;  // one launch, one buffer flip
+                done += n;
+                runs0 += n;
+                if (c->res_limit > 0) { c->res_limit = 0; c->force_stream = 1; }
+            } else {
+                const int k = (int)(key >> KEY_STEP_SHIFT);
+                if (k > 0) c->res_limit = k;
+                else c->force_stream = 1;
+            }
+        } else {
+            int ok = n;
+            if (key != NO_EVENT) ok = (int)(key >> KEY_STEP_SHIFT);
+            if (ok > 0) c->entries.clear();  // entries belonged to the batch's first step
+            c->cur = (c->cur + ok) & 1;
+            done += ok;
+            runs0 += ok;
+            if (c->force_stream > 0) c->force_stream = std::max(0, c->force_stream - ok);
+            if (key != NO_EVENT) {
+                const int chain = (int)((key >> KEY_CHAIN_SHIFT) & 0x3FFF);
+                const u64 g = key & ((1ULL << KEY_CHAIN_SHIFT) - 1);
+                u64 S;
+                CK(cudaMemcpy(&S, c->l_seeds[c->cur] + chain, sizeof(u64), cudaMemcpyDeviceToHost));
+                const u64 sfull = host_seed_before(c, c->entries, chain, S, g);
+                const HostDraw h = host_draw_literal(sfull, g);
+                RebaseEntry e{};
+                e.gid_start = g + 1;
+                e.seed = h.seed_after;
+                e.ov_gid = g;
+                e.ov_t1 = h.t1;
+                e.ov_t2 = h.t2;
+                e.chain = chain;
+                if ((int)c->entries.size() >= MAX_REBASE) return SQ_ERR_INVALID;
+                c->entries.push_back(e);
+                c->nevents++;
+                CK(cudaMemcpy(c->l_rebase, c->entries.data(), sizeof(RebaseEntry) * c->entries.size(),
+                              cudaMemcpyHostToDevice));
+                if (c->force_stream == 0) c->force_stream = 1;  // the step with entries is a streaming step
+            }
+        }
         if (key != NO_EVENT) {
-            const int chain = (int)((key >> KEY_CHAIN_SHIFT) & 0x3FFF);
-            const u64 g = key & ((1ULL << KEY_CHAIN_SHIFT) - 1);
-            u64 S;
-            CK(cudaMemcpy(&S, c->l_seeds[c->cur] + chain, sizeof(u64), cudaMemcpyDeviceToHost));
-            const u64 sfull = host_seed_before(c, c->entries, chain, S, g);
-            const HostDraw h = host_draw_literal(sfull, g);
-            RebaseEntry e{};
-            e.gid_start = g + 1;
-            e.seed = h.seed_after;
-            e.ov_gid = g;
-            e.ov_t1 = h.t1;
-            e.ov_t2 = h.t2;
-            e.chain = chain;
-            if ((int)c->entries.size() >= MAX_REBASE) return SQ_ERR_INVALID;
-            c->entries.push_back(e);
-            c->nevents++;
-            CK(cudaMemcpy(c->l_rebase, c->entries.data(), sizeof(RebaseEntry) * c->entries.size(),
-                          cudaMemcpyHostToDevice));
             const u64 none = NO_EVENT;
             CK(cudaMemcpy(c->l_event, &none, sizeof(u64), cudaMemcpyHostToDevice));
         }
-        const int remaining = total_steps - done;
-        if (remaining <= 0) break;
-        const int n = std::min(remaining, MAX_SEQ_STEPS);
-        int rc = enqueue_lattice(c, c->pend_dtau, n, runs0);
+        if (done >= total) break;
+        int rc = enqueue_batch(c, total - done, runs0);
         if (rc) return rc;
-        c->pend_nsteps = n;
     }
     c->entries.clear();
+    c->force_stream = 0;
+    c->res_limit = 0;
     c->runs = runs0;
     c->last_stable = 1;
     c->last_steps = done;
@@ -537,7 +674,7 @@ extern "C" int sq_sync(sq_ctx *c, int *stable) {
             }
         }
     } else {
-        rc = sync_lattice(c, c->pend_total);
+        rc = sync_lattice(c);
         if (rc) { c->pending = false; return rc; }
     }
     c->pending = false;
@@ -696,6 +833,10 @@ extern "C" int sq_set_chain(sq_ctx *c, int chain, uint64_t seed, double m2, doub
     CK(cudaMemcpy(c->l_seeds[c->cur] + chain, &seed, sizeof(u64), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->l_m2 + chain, &m2, sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->l_lam + chain, &lambda, sizeof(double), cudaMemcpyHostToDevice));
+    if (chain == 0) {  // host mirror: the resident kernel takes the couplings by value
+        c->p.m2 = m2;
+        c->p.lambda = lambda;
+    }
     return SQ_OK;
 }
 

@@ -98,6 +98,39 @@ cudaError_t launch_finalize(const FinalizeArgs &A, cudaStream_t stream);
 
 cudaError_t launch_debug_draws(u64 seed, u64 gid0, u64 n, const JumpEntry *jump, u64 *t1, u64 *t2,
                                cudaStream_t stream);
+// ---------------------------------------------------------------- resident 2-D ---
+struct ResidentArgs {
+    int L0, L1, nsteps, pot;
+    int step_index0;     // sequence index of the launch's first step (event key)
+    unsigned step0;      // flag value all CTAs start from
+    long long V;
+    const float *in;
+    float *out;
+    float *halo;         // [2][nblocks][2][L0]
+    unsigned *flags;     // [nblocks] steps published
+    double c_lap, c_dt, nscale, m2, lam;
+    const u64 *seed_in;
+    u64 *seed_out;
+    u64 P, Q;            // whole-step affine seed advance over V+1 draws
+    JumpEntry vol_jump;  // jump over V draws from gid 0
+    const JumpEntry *jump;
+    u64 *event_key;
+    double *hist_rows;   // [nsteps][L1] slice sums of the pre-update field
+    double *hist_p2;     // [nsteps][nblocks] partial sums of phi^2
+    unsigned long long *nclamped;
+    unsigned *error_flag;
+};
+cudaError_t launch_resident2d(const ResidentArgs &A, int math, int nblocks, int rows_max, cudaStream_t st);
+
+struct WelfordArgs {
+    int nt, nsteps, tmid, np2;
+    long long vslice, runs;
+    const double *hist_rows, *hist_p2;
+    double *slice_x, *slice_xx0, *slice_sum, *sums, *sums_mean;
+    const u64 *event_key;
+};
+cudaError_t launch_welford_history(const WelfordArgs &A, cudaStream_t stream);
+
 // current-configuration reductions: partial sums [nchains][nblocks][2] (phi, phi^2), fixed order
 constexpr int REDUCE_BLOCKS = 256;
 cudaError_t launch_reduce_field(const void *field, int real, long long nper_chain, int nchains,

@@ -30,16 +30,19 @@ __device__ __forceinline__ float u32_to_f32_rn(unsigned u) {
 }
 
 // FAST: r = cos(2*3.1415*v2) * sqrt(-2 ln v1), fp32 + SFU.
-//   ln v1 = ln2 * (log2((float)u1) - 32)                      MUFU.LG2
+//   ln v1 = ln2 * log2(v1), v1 = (float)u1 * 2^-32 (exact scaling): MUFU.LG2 directly on v1 keeps
+//   its 2^-22 absolute error where v1 -> 1 (no "32 - log2(u1)" cancellation).
 //   cos(theta), theta = 2*3.1415*v2 in [0, 6.283): MUFU.COS wants |x| <= pi for its
 //   2^-21.4 abs error, so evaluate -cos(theta - pi).
+// Error vs the reference-literal value: |dr| <~ 1e-6 typically; for draws with v1 > 1-2^-12
+// (p = 2.4e-4) the sqrt of a small argument amplifies the SFU's absolute log error: |dr| <= ~5e-5,
+// worst case ~1e-3 when v1 = 1-2^-32.
 __device__ __forceinline__ float noise_fast(u64 t1, u64 t2) {
     const unsigned u1 = (unsigned)(t1 >> 16), u2 = (unsigned)(t2 >> 16);
-    const float f1 = u32_to_f32_rn(u1);  // == (float)v1 * 2^32 (power-of-two scaling is exact)
+    const float v1 = u32_to_f32_rn(u1) * 2.3283064365386963e-10f;  // == (float)v1 of :274
     const float f2 = u32_to_f32_rn(u2);
-    // -2 ln v1 = -2 ln2 (log2 f1 - 32) ; clamp at 0: v1 may round to 1.0f and the SFU
-    // may return a tiny positive log there
-    const float m2l = fmaxf(0.0f, (32.0f - __log2f(f1)) * 1.3862943611198906f);
+    // clamp at 0: v1 may round to 1.0f and the SFU may return a tiny positive log there
+    const float m2l = fmaxf(0.0f, __log2f(v1) * -1.3862943611198906f);  // -2 ln2 log2 v1
     const float rad = __fsqrt_rn(m2l);
     const float th = __fmaf_rn(f2, (float)(2. * 3.1415 / 4294967296.0), -3.14159265358979f);
     return -__cosf(th) * rad;

@@ -1,0 +1,75 @@
+// sq_site.cuh -- the per-site inner pipeline shared by the lattice kernels, written for issue
+// slots: the fused Langevin step is instruction-bound on B200 (ncu, profiles/), not HBM-bound.
+//
+//   RNG   (tau_kernel.cl:273-281)  two 48-bit LCG steps as 32-bit limbs: 12 integer ops / site
+//   noise (tau_kernel.cl:274-277)  FAST: 4 SFU ops + ~8 FMA/ALU ops;  ACCURATE: reference casts
+//   events                         detected for ~2 ops / site, resolved on a cold path
+//
+// The 48-bit seed s is carried as (sl, sh); only bits 0..47 are meaningful, higher bits of sh are
+// garbage that never reaches a result (every consumer takes bits <= 47).
+#pragma once
+#include "sq_lcg.cuh"
+#include "sq_noise.cuh"
+
+namespace sq {
+
+constexpr unsigned A_LO = 0xDEECE66Du, A_HI = 0x5u;
+
+struct Seed32 {
+    unsigned lo, hi;
+};
+__device__ __forceinline__ Seed32 seed_split(u64 s) { return Seed32{(unsigned)s, (unsigned)(s >> 32)}; }
+__device__ __forceinline__ u64 seed_join(Seed32 s) { return (((u64)s.hi << 32) | s.lo) & LCG_MASK; }
+
+// x*A + c  (mod 2^64 in the low word, bits 32..47 valid in the high word)
+__device__ __forceinline__ void mad48(unsigned xl, unsigned xh, unsigned cl, unsigned ch, unsigned &rl, unsigned &rh) {
+    const u64 p = (u64)xl * A_LO + (((u64)ch << 32) | cl);  // IMAD.WIDE.U32 with 64-bit addend
+    rl = (unsigned)p;
+    rh = (unsigned)(p >> 32) + xl * A_HI + xh * A_LO;        // 2 x IMAD
+}
+
+// One draw at the site whose constant is c = gid*A + B.  Returns u1 = t1>>16, u2 = t2>>16 (32 bits
+// each) and advances the seed to t2 - 2^31 (event-free path, :281).
+__device__ __forceinline__ void site_draw(Seed32 &s, unsigned cl, unsigned ch, unsigned &u1, unsigned &u2) {
+    unsigned t1l, t1h, t2l, t2h;
+    mad48(s.lo, s.hi, cl, ch, t1l, t1h);      // t1 = (s+g)A + B = sA + c
+    u1 = __funnelshift_r(t1l, t1h, 16);
+    mad48(t1l, t1h, cl, ch, t2l, t2h);        // t2 = (t1+g)A + B = t1 A + c
+    u2 = __funnelshift_r(t2l, t2h, 16);
+    s.lo = t2l + 0x80000000u;                 // t2 - 2^31
+    s.hi = t2h - (t2l < 0x80000000u ? 1u : 0u);
+}
+// c for the next gid: c += A
+__device__ __forceinline__ void site_const_next(unsigned &cl, unsigned &ch) {
+    const u64 c = ((((u64)ch << 32) | cl)) + LCG_A;
+    cl = (unsigned)c;
+    ch = (unsigned)(c >> 32);
+}
+__device__ __forceinline__ void site_const(u64 gid, unsigned &cl, unsigned &ch) {
+    const u64 c = gid * LCG_A + LCG_B;
+    cl = (unsigned)c;
+    ch = (unsigned)(c >> 32);
+}
+
+// Cheap necessary condition for an RNG event at this draw, given what the hot path has anyway:
+//   inf-retry  <=> u1 == 0
+//   `seed+=`    => t2 < 2^31 <=> u2 < 2^15
+__device__ __forceinline__ bool site_maybe_event(unsigned u1, unsigned u2) { return (u1 == 0u) | (u2 < 32768u); }
+
+// FAST noise amplitude: returns r * scale where r = cos(2*3.1415 v2) sqrt(-2 ln v1) and
+// k2 = 2 ln2 * scale^2 (scale folded under the square root).
+//   v1: exact RN conversion on the conversion unit (I2F), scaled by 2^-32 (exact)
+//   v2: top 23 bits of u2 through the exponent trick (ALU), |d theta| <= 7.5e-7
+__device__ __forceinline__ float site_noise_fast(unsigned u1, unsigned u2, float k2) {
+    const float v1 = __uint2float_rn(u1) * 2.3283064365386963e-10f;
+    float lg;                                           // MUFU.LG2 (v1 >= 2^-32: never denormal)
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(v1));
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(fabsf(lg * k2)));
+    const float f = __uint_as_float(0x3F800000u | (u2 >> 9));  // [1,2): 1 + v2 (23 bits)
+    // theta - pi = 2*3.1415*(f-1) - pi
+    const float th = __fmaf_rn(f, 6.283f, -6.283f - 3.14159265358979f);
+    return -__cosf(th) * rad;                           // cos(theta) = -cos(theta - pi)
+}
+
+}  // namespace sq
