@@ -67,9 +67,10 @@ struct sq_ctx {
     // resident 2-D path (sq_resident.cu)
     bool res_ok = false;
     int res_nb = 0, res_rows = 0;
-    float *r_halo = nullptr;
-    unsigned *r_flags = nullptr, *r_error = nullptr;
-    double *r_hist_rows = nullptr, *r_hist_p2 = nullptr;
+    unsigned long long *r_halo = nullptr;
+    unsigned *r_error = nullptr;
+    unsigned r_tag = 1;     // monotonic halo tag base (never reused, also across replays)
+    double *r_hist_rows = nullptr, *r_hist_p2 = nullptr, *r_step_sums = nullptr;
     int res_limit = 0;      // >0: the next resident batch must stop after this many steps
     int force_stream = 0;   // >0: this many steps must go through the streaming kernel
     int pend_kind = 0;      // 0 streaming, 1 resident
@@ -165,7 +166,7 @@ extern "C" void sq_free(sq_ctx *c) {
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
                     c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped,
-                    c->r_halo, c->r_flags, c->r_error, c->r_hist_rows, c->r_hist_p2};
+                    c->r_halo, c->r_error, c->r_hist_rows, c->r_hist_p2, c->r_step_sums};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -298,11 +299,11 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
                 c->res_ok = true;
                 c->res_nb = nb;
                 c->res_rows = rows;
-                CK(cudaMalloc((void **)&c->r_halo, sizeof(float) * 2 * (size_t)nb * 2 * (size_t)L0));
-                if ((rc = dalloc(&c->r_flags, (size_t)nb))) return rc;
+                if ((rc = dalloc(&c->r_halo, 2 * (size_t)nb * 2 * (size_t)L0))) return rc;
                 if ((rc = dalloc(&c->r_error, 1))) return rc;
                 if ((rc = dalloc(&c->r_hist_rows, (size_t)RES_MAX_STEPS * (size_t)L1))) return rc;
                 if ((rc = dalloc(&c->r_hist_p2, (size_t)RES_MAX_STEPS * (size_t)nb))) return rc;
+                if ((rc = dalloc(&c->r_step_sums, (size_t)RES_MAX_STEPS * 2))) return rc;
             }
         }
     }
@@ -471,12 +472,12 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     A.nsteps = nsteps;
     A.pot = p.potential;
     A.step_index0 = 0;
-    A.step0 = 0;
+    A.step0 = c->r_tag;
+    c->r_tag += (unsigned)nsteps + 1u;
     A.V = c->V;
     A.in = (const float *)c->l_field[c->cur];
     A.out = (float *)c->l_field[c->cur ^ 1];
-    A.halo = c->r_halo;
-    A.flags = c->r_flags;
+    A.halo_ll = c->r_halo;
     A.c_lap = L.c_lap;
     A.c_dt = L.c_dt;
     A.nscale = L.nscale;
@@ -496,7 +497,6 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     A.error_flag = c->r_error;
     // per-chain couplings live in device arrays for the streaming kernel; the resident kernel is
     // single-chain and takes them by value: keep both in sync through sq_set_chain (host mirror)
-    CK(cudaMemsetAsync(c->r_flags, 0, sizeof(unsigned) * (size_t)c->res_nb, c->stream));
     if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
     CK(launch_resident2d(A, p.math, c->res_nb, c->res_rows, c->stream));
     if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
@@ -516,8 +516,8 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     W.sums = c->l_sums;
     W.sums_mean = c->l_sums_mean;
     W.event_key = c->l_event;
-    CK(launch_welford_history(W, c->stream));
-    c->launches++;
+    CK(launch_welford_history(W, c->r_step_sums, c->stream));
+    c->launches += 2;
     return SQ_OK;
 }
 

@@ -102,12 +102,11 @@ cudaError_t launch_debug_draws(u64 seed, u64 gid0, u64 n, const JumpEntry *jump,
 struct ResidentArgs {
     int L0, L1, nsteps, pot;
     int step_index0;     // sequence index of the launch's first step (event key)
-    unsigned step0;      // flag value all CTAs start from
+    unsigned step0;      // tag base: tags step0+1.. are unique within the context
     long long V;
     const float *in;
     float *out;
-    float *halo;         // [2][nblocks][2][L0]
-    unsigned *flags;     // [nblocks] steps published
+    unsigned long long *halo_ll;  // [2][nblocks][2][L0] words {float bits, step tag}
     double c_lap, c_dt, nscale, m2, lam;
     const u64 *seed_in;
     u64 *seed_out;
@@ -129,7 +128,7 @@ struct WelfordArgs {
     double *slice_x, *slice_xx0, *slice_sum, *sums, *sums_mean;
     const u64 *event_key;
 };
-cudaError_t launch_welford_history(const WelfordArgs &A, cudaStream_t stream);
+cudaError_t launch_welford_history(const WelfordArgs &A, double *step_sums /* [2*nsteps] scratch */, cudaStream_t stream);
 
 // current-configuration reductions: partial sums [nchains][nblocks][2] (phi, phi^2), fixed order
 constexpr int REDUCE_BLOCKS = 256;

@@ -64,11 +64,11 @@ struct SiteCoef {
 
 // new value of one site.  nsum = sum of the 4 neighbours in the oracle's order (+0,-0,+1,-1).
 // Operation order is part of the definition of the fp32 lattice update ("lattice update").
-template <int MATH>
+template <int MATH, int POT>
 __device__ __forceinline__ float site_update(float phi, float nsum, unsigned u1, unsigned u2, const SiteCoef &C) {
     const float lap = __fmaf_rn(-4.0f, phi, nsum);
     float v = __fmaf_rn(C.c_lap, lap, phi);
-    if (C.pot == 4) {
+    if (POT == 4) {
         const float F = __fmul_rn(phi, __fmaf_rn(C.lam, __fmul_rn(phi, phi), C.m2));
         v = __fmaf_rn(-C.c_dt, F, v);
     } else {
@@ -83,15 +83,127 @@ __device__ __forceinline__ float site_update(float phi, float nsum, unsigned u1,
 
 }  // namespace
 
-// NR = rows actually owned by this CTA (compile-time so the band stays in registers)
-template <int NR, int MATH>
-__device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, float *smem) {
-    const int T = blockDim.x, t = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
-    const int L0 = A.L0;
+// named barriers (id 0 is __syncthreads and is not used once the roles split)
+constexpr int BAR_EDGES = 1;   // compute warps only: shared-memory edges / row sums handed over
+constexpr int BAR_CONSUMED = 2; // compute arrive, comm warp sync: this step's staged rows have been read
+constexpr int BAR_HALO = 3;    // comm warp arrive, compute sync: neighbours' rows are in shared memory
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// 16-byte load of two {float bits, tag} words; each 64-bit element is a single-copy-atomic scalar
+__device__ __forceinline__ ulonglong2 ld_relaxed_ll(const unsigned long long *p) {
+    ulonglong2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ll_pack(float v, unsigned tag) {
+    return ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+}
+
+// ---- the communication warp: receive the neighbours' boundary rows (flag-in-data), stage them ---
+// Halo protocol: every boundary value travels as one 64-bit word {float, step tag}.  A word whose
+// tag equals the expected step IS the data of that step (64-bit scalar accesses are single-copy
+// atomic), so the producer needs no fence and no separate flag, the consumer no acquire:
+// one L2 write + one L2 read of latency.  Tags never repeat within a context (step0 is monotonic,
+// also across replayed launches).
+__device__ __forceinline__ void resident_comm_warp(const ResidentArgs &A, float *hbuf, int r0, int nr, int T) {
+    const int lane = threadIdx.x & 31, b = blockIdx.x, nb = gridDim.x, L0 = A.L0;
     const int bup = (b + 1 == nb) ? 0 : b + 1, bdn = (b == 0) ? nb - 1 : b - 1;
-    // shared: edges [2 buffers][NR rows][2 (first,last)][T] ; row-sum transpose [NR+1][T]
+    const int nall = T + 32;
+    // prologue: halo rows of the initial field, straight from the input buffer
+    {
+        const int rup = (r0 + nr == A.L1) ? 0 : r0 + nr, rdn = (r0 == 0) ? A.L1 - 1 : r0 - 1;
+        for (int i = lane * 4; i < L0; i += 128) {
+            *reinterpret_cast<float4 *>(hbuf + i) = *reinterpret_cast<const float4 *>(A.in + (size_t)rdn * L0 + i);
+            *reinterpret_cast<float4 *>(hbuf + L0 + i) = *reinterpret_cast<const float4 *>(A.in + (size_t)rup * L0 + i);
+        }
+        __threadfence_block();
+        bar_arrive(BAR_HALO, nall);
+    }
+    Seed32 Som = seed_split(A.seed_in[0]);
+    unsigned failed = 0;
+    for (int n = 0; n < A.nsteps; ++n) {
+        if (n + 1 < A.nsteps) {
+            const unsigned want = A.step0 + (unsigned)n + 1u;
+            const unsigned long long *hb = A.halo_ll + (size_t)((n + 1) & 1) * nb * 2 * L0;
+            const unsigned long long *src_dn = hb + ((size_t)bdn * 2 + 1) * L0;  // neighbour below: its LAST row
+            const unsigned long long *src_up = hb + ((size_t)bup * 2 + 0) * L0;  // neighbour above: its FIRST row
+            // lane handles pairs of sites i, i+1 with i = j*64 + lane*2  (L0 <= 1024: j < 16)
+            ulonglong2 d[16], u[16];
+            unsigned pending = 0xFFFFFFFFu, spins = 0;
+            while (pending) {
+                unsigned still = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int i = j * 64 + lane * 2;
+                    if (i < L0 && (pending & (1u << j))) d[j] = ld_relaxed_ll(src_dn + i);
+                    if (i < L0 && (pending & (0x10000u << j))) u[j] = ld_relaxed_ll(src_up + i);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int i = j * 64 + lane * 2;
+                    if (i < L0) {
+                        if ((unsigned)(d[j].x >> 32) != want || (unsigned)(d[j].y >> 32) != want) still |= 1u << j;
+                        if ((unsigned)(u[j].x >> 32) != want || (unsigned)(u[j].y >> 32) != want) still |= 0x10000u << j;
+                    }
+                }
+                pending = still;
+                if (pending) {
+                    ++spins;
+                    // the launch is being abandoned (an RNG event must be replayed): stop waiting
+                    if ((spins & 15u) == 0 && *((volatile const u64 *)A.event_key) != NO_EVENT) break;
+                    if (spins > (1u << 20)) { failed = 1; break; }  // never hang the GPU
+                }
+            }
+            // the compute warps have finished reading the buffer we are about to overwrite
+            bar_sync(BAR_CONSUMED, nall);
+            float *dst = hbuf + (size_t)((n + 1) & 1) * 2 * L0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int i = j * 64 + lane * 2;
+                if (i < L0) {
+                    *reinterpret_cast<float2 *>(dst + i) =
+                        make_float2(__uint_as_float((unsigned)d[j].x), __uint_as_float((unsigned)d[j].y));
+                    *reinterpret_cast<float2 *>(dst + L0 + i) =
+                        make_float2(__uint_as_float((unsigned)u[j].x), __uint_as_float((unsigned)u[j].y));
+                }
+            }
+            __threadfence_block();
+            bar_arrive(BAR_HALO, nall);
+        }
+        // the omega work-item's draw (gid = V), tau_kernel.cl:103-110
+        if (b == 0 && lane == 0) {
+            const u64 S = seed_join(Som);
+            const u64 sV = lcg_apply(A.vol_jump, S, 0) & LCG_MASK;
+            u64 t1, t2;
+            lcg_draw(sV, (u64)A.V, t1, t2);
+            if (lcg_event(sV, t1, t2))
+                atomicMin((unsigned long long *)A.event_key, event_key(A.step_index0 + n, 0, (u64)A.V));
+            Som = seed_split(lcg_next_seed(t2));
+            if (n == A.nsteps - 1) A.seed_out[0] = lcg_next_seed(t2);
+        }
+    }
+    if (__any_sync(0xffffffffu, failed) && lane == 0) atomicExch(A.error_flag, 1u);
+}
+
+// ---- compute warps.  NR = rows owned by this CTA (compile-time: the band stays in registers) ---
+// TT = compile-time threads per row (0: runtime) so shared-memory offsets become immediates.
+template <int NR, int MATH, int POT, int TT>
+__device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, float *smem, float *hbuf) {
+    const int T = TT ? TT : (int)blockDim.x - 32;
+    const int t = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
+    const int L0 = A.L0;
+    const int nall = T + 32;
+    // shared: edges [2 buffers][NR rows][2 (first,last)][T] ; row-sum transpose [2][NR+1][T] ;
+    // per-strip chain state [NR][T] x {seed lo, seed hi, K lo, K hi} (kept out of the register file)
     float *edge = smem;
-    float *rs = smem + 2 * NR * 2 * T;
+    float *rs_all = smem + 2 * NR * 2 * T;
+    uint4 *chain = reinterpret_cast<uint4 *>(rs_all + 2 * (NR + 1) * T);
     SiteCoef C;
     C.c_lap = (float)A.c_lap;
     C.pot = A.pot;
@@ -104,8 +216,6 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
 
     // ---- load the band, set up the per-strip chain state -----------------------------------
     float phi[NR][4];
-    Seed32 sd[NR];
-    unsigned Kl[NR], Kh[NR];
     const u64 S0 = A.seed_in[0];
     const u64 S1 = (A.P * S0 + A.Q) & LCG_MASK;  // predicted seed after one whole step
 #pragma unroll
@@ -116,9 +226,7 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
         const u64 s0 = lcg_seed_at(S0, 0, g, A.jump);
         const u64 s1 = lcg_seed_at(S1, 0, g, A.jump);
         const u64 K = (s1 - A.P * s0) & LCG_MASK;
-        sd[k] = seed_split(s0);
-        Kl[k] = (unsigned)K;
-        Kh[k] = (unsigned)(K >> 32);
+        chain[k * T + t] = make_uint4((unsigned)s0, (unsigned)(s0 >> 32), (unsigned)K, (unsigned)(K >> 32));
     }
     const unsigned Pl = (unsigned)A.P, Ph = (unsigned)(A.P >> 32);
     // c = gid*A + B of the first site of row 0's strip; rows advance it by L0*A
@@ -126,35 +234,23 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
     site_const((u64)r0 * L0 + 4 * t, c0l, c0h);
     const u64 rowA = (u64)L0 * LCG_A;
 
-    // halo rows of the current field: from the neighbours' input rows
-    float hup[4], hdn[4];
-    {
-        const int rup = (r0 + NR == A.L1) ? 0 : r0 + NR, rdn = (r0 == 0) ? A.L1 - 1 : r0 - 1;
-        const float4 u = *reinterpret_cast<const float4 *>(A.in + (size_t)rup * L0 + 4 * t);
-        const float4 d = *reinterpret_cast<const float4 *>(A.in + (size_t)rdn * L0 + 4 * t);
-        hup[0] = u.x; hup[1] = u.y; hup[2] = u.z; hup[3] = u.w;
-        hdn[0] = d.x; hdn[1] = d.y; hdn[2] = d.z; hdn[3] = d.w;
-    }
     // edges of the initial field
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
         edge[((0 * NR + k) * 2 + 0) * T + t] = phi[k][0];
         edge[((0 * NR + k) * 2 + 1) * T + t] = phi[k][3];
     }
-    __syncthreads();
+    bar_sync(BAR_EDGES, T);
 
     const int tl = (t == 0) ? T - 1 : t - 1, tr = (t + 1 == T) ? 0 : t + 1;
-    Seed32 Som = seed_split(S0);  // only used by (b==0,t==0): the step-start seed
     unsigned myclamp = 0;
-    unsigned failed = 0;
 
     for (int n = 0; n < A.nsteps; ++n) {
         const int eb = n & 1;
-        float psum[NR];   // per-thread sums of the pre-update row values
+        float *rs = rs_all + (size_t)eb * (NR + 1) * T;  // double-buffered: last step's is being reduced
         float p2 = 0.f;
-        float nw[NR][4];  // new values
-        // ---- one row: draws + update -----------------------------------------------------
-        auto do_row = [&](int k, const float *up, const float *dn) {
+        // ---- one row: draws + update; returns the new values in out[] -----------------------
+        auto do_row = [&](int k, const float *cur, const float *up, const float *dn, float *out) {
             const float left = edge[((eb * NR + k) * 2 + 1) * T + tl];
             const float right = edge[((eb * NR + k) * 2 + 0) * T + tr];
             unsigned cl, ch;
@@ -163,7 +259,8 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
                 cl = (unsigned)c;
                 ch = (unsigned)(c >> 32);
             }
-            Seed32 s = sd[k];
+            const uint4 st = chain[k * T + t];
+            Seed32 s{st.x, st.y};
             const Seed32 s_before = s;
             float a = 0.f;
             bool maybe = false;
@@ -173,86 +270,84 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
                 site_draw(s, cl, ch, u1, u2);
                 site_const_next(cl, ch);
                 maybe |= site_maybe_event(u1, u2);
-                const float p = phi[k][e];
-                const float xp = (e < 3) ? phi[k][(e + 1) & 3] : right;
-                const float xm = (e > 0) ? phi[k][(e + 3) & 3] : left;
+                const float p = cur[e];
+                const float xp = (e < 3) ? cur[(e + 1) & 3] : right;
+                const float xm = (e > 0) ? cur[(e + 3) & 3] : left;
                 const float nsum = __fadd_rn(__fadd_rn(__fadd_rn(xp, xm), up[e]), dn[e]);
-                nw[k][e] = site_update<MATH>(p, nsum, u1, u2, C);
+                out[e] = site_update<MATH, POT>(p, nsum, u1, u2, C);
                 a = __fadd_rn(a, p);
                 p2 = __fmaf_rn(p, p, p2);
-                if (fabsf(nw[k][e]) >= 1000.0f) ++myclamp;
             }
-            psum[k] = a;
+            // clamp hits (tau_kernel.cl:122-132) are counted on a cold path
+            if (__builtin_expect(fmaxf(fmaxf(fabsf(out[0]), fabsf(out[1])), fmaxf(fabsf(out[2]), fabsf(out[3]))) >= 1000.0f, 0)) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) myclamp += (fabsf(out[e]) >= 1000.0f) ? 1u : 0u;
+            }
+            rs[k * T + t] = a;
             if (__builtin_expect(maybe, 0))
                 strip_events_cold(A.event_key, A.step_index0 + n, seed_join(s_before), (u64)(r0 + k) * L0 + 4 * t);
             // the strip keeps its gids: next step's seed by one affine map (5 integer ops)
-            unsigned nl, nh;
-            {
-                const u64 p = (u64)sd[k].lo * Pl + (((u64)Kh[k] << 32) | Kl[k]);
-                nl = (unsigned)p;
-                nh = (unsigned)(p >> 32) + sd[k].lo * Ph + sd[k].hi * Pl;
-            }
-            sd[k].lo = nl;
-            sd[k].hi = nh;
+            const u64 p = (u64)st.x * Pl + (((u64)st.w << 32) | st.z);
+            const unsigned nh = (unsigned)(p >> 32) + st.x * Ph + st.y * Pl;
+            *reinterpret_cast<uint2 *>(&chain[k * T + t]) = make_uint2((unsigned)p, nh);
         };
 
-        // ---- phase A: the two boundary rows first, publish them --------------------------
-        if (NR == 1) {
-            do_row(0, hup, hdn);
-        } else {
-            do_row(0, phi[1], hdn);
-            do_row(NR - 1, hup, phi[NR - 2]);
-        }
+        // ---- neighbours' rows of the current field, staged by the comm warp ------------------
+        bar_sync(BAR_HALO, nall);
+        float hdn[4], hup[4];
         {
-            float *ho = A.halo + ((size_t)((n + 1) & 1) * nb + b) * 2 * L0;
-            *reinterpret_cast<float4 *>(ho + 4 * t) = make_float4(nw[0][0], nw[0][1], nw[0][2], nw[0][3]);
-            *reinterpret_cast<float4 *>(ho + L0 + 4 * t) =
-                make_float4(nw[NR - 1][0], nw[NR - 1][1], nw[NR - 1][2], nw[NR - 1][3]);
-            __threadfence();
+            const float4 d = *reinterpret_cast<const float4 *>(hbuf + (size_t)eb * 2 * L0 + 4 * t);
+            const float4 u = *reinterpret_cast<const float4 *>(hbuf + (size_t)eb * 2 * L0 + L0 + 4 * t);
+            hdn[0] = d.x; hdn[1] = d.y; hdn[2] = d.z; hdn[3] = d.w;
+            hup[0] = u.x; hup[1] = u.y; hup[2] = u.z; hup[3] = u.w;
         }
-        __syncthreads();
-        if (t == 0) st_release_u32(A.flags + b, A.step0 + (unsigned)n + 1u);
+        if (n + 1 < A.nsteps) bar_arrive(BAR_CONSUMED, nall);
 
-        // ---- phase B: interior rows; prefetch the neighbours' new boundary rows -----------
-        float nup[4], ndn[4];
-        bool fetched = false;
-        auto fetch_halo = [&]() {
-            const unsigned want = A.step0 + (unsigned)n + 1u;
-            unsigned spins = 0;
-            while ((int)(ld_volatile_u32(A.flags + bup) - want) < 0 || (int)(ld_volatile_u32(A.flags + bdn) - want) < 0) {
-                ++spins;
-                // the launch is being abandoned (an RNG event must be replayed): stop waiting
-                if ((spins & 63u) == 0 && *((volatile const u64 *)A.event_key) != NO_EVENT) break;
-                if (spins > (1u << 21)) { failed = 1; break; }  // ~1 s: never hang the GPU
-            }
-            const float *hb = A.halo + (size_t)((n + 1) & 1) * nb * 2 * L0;
-            const float4 u = ld_cg_f4(hb + (size_t)bup * 2 * L0 + 4 * t);        // neighbour above: its FIRST row
-            const float4 d = ld_cg_f4(hb + (size_t)bdn * 2 * L0 + L0 + 4 * t);   // neighbour below: its LAST row
-            nup[0] = u.x; nup[1] = u.y; nup[2] = u.z; nup[3] = u.w;
-            ndn[0] = d.x; ndn[1] = d.y; ndn[2] = d.z; ndn[3] = d.w;
-            fetched = true;
-        };
+        // ---- phase A: the two boundary rows first, publish them (fire and forget) -----------
+        float first[4], last[4];
+        if (NR == 1) {
+            do_row(0, phi[0], hup, hdn, first);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) last[e] = first[e];
+        } else {
+            do_row(0, phi[0], phi[1], hdn, first);
+            do_row(NR - 1, phi[NR - 1], hup, phi[NR - 2], last);
+        }
+        if (n + 1 < A.nsteps) {  // {value, tag} words: no fence, no flag (see resident_comm_warp)
+            const unsigned tag = A.step0 + (unsigned)n + 1u;
+            unsigned long long *ho = A.halo_ll + ((size_t)((n + 1) & 1) * nb + b) * 2 * L0 + 4 * t;
+            *reinterpret_cast<ulonglong2 *>(ho) = make_ulonglong2(ll_pack(first[0], tag), ll_pack(first[1], tag));
+            *reinterpret_cast<ulonglong2 *>(ho + 2) = make_ulonglong2(ll_pack(first[2], tag), ll_pack(first[3], tag));
+            *reinterpret_cast<ulonglong2 *>(ho + L0) = make_ulonglong2(ll_pack(last[0], tag), ll_pack(last[1], tag));
+            *reinterpret_cast<ulonglong2 *>(ho + L0 + 2) = make_ulonglong2(ll_pack(last[2], tag), ll_pack(last[3], tag));
+        }
+
+        // ---- phase B: interior rows, in place (old copies of the rows still needed below) ----
+        float prev[4];  // old values of row k-1
+#pragma unroll
+        for (int e = 0; e < 4; ++e) prev[e] = phi[0][e];
 #pragma unroll
         for (int k = 1; k < NR - 1; ++k) {
-            do_row(k, phi[k + 1], phi[k - 1]);
-            if (k == (NR - 1) / 2) fetch_halo();
+            float out[4];
+            do_row(k, phi[k], phi[k + 1], prev, out);  // phi[k+1] is still old (row NR-1 lives in `last`)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { prev[e] = phi[k][e]; phi[k][e] = out[e]; }
         }
-        if (!fetched) fetch_halo();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            phi[0][e] = first[e];
+            if (NR > 1) phi[NR - 1][e] = last[e];
+        }
 
-        // ---- hand-over: registers, edges, row sums ----------------------------------------
+        // ---- hand-over: edges, row sums -------------------------------------------------------
         const int nbuf = eb ^ 1;
 #pragma unroll
         for (int k = 0; k < NR; ++k) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) phi[k][e] = nw[k][e];
-            edge[((nbuf * NR + k) * 2 + 0) * T + t] = nw[k][0];
-            edge[((nbuf * NR + k) * 2 + 1) * T + t] = nw[k][3];
-            rs[k * T + t] = psum[k];
+            edge[((nbuf * NR + k) * 2 + 0) * T + t] = phi[k][0];
+            edge[((nbuf * NR + k) * 2 + 1) * T + t] = phi[k][3];
         }
         rs[NR * T + t] = p2;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { hup[e] = nup[e]; hdn[e] = ndn[e]; }
-        __syncthreads();
+        bar_sync(BAR_EDGES, T);
 
         // ---- per-row sums: warp w reduces row w (and the phi^2 column) ---------------------
         {
@@ -268,18 +363,6 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
                 }
             }
         }
-
-        // ---- the omega work-item's draw (gid = V) ------------------------------------------
-        if (b == 0 && t == 0) {
-            const u64 S = seed_join(Som);
-            const u64 sV = lcg_apply(A.vol_jump, S, 0) & LCG_MASK;
-            u64 t1, t2;
-            lcg_draw(sV, (u64)A.V, t1, t2);
-            if (lcg_event(sV, t1, t2))
-                atomicMin((unsigned long long *)A.event_key, event_key(A.step_index0 + n, 0, (u64)A.V));
-            Som = seed_split(lcg_next_seed(t2));
-            if (n == A.nsteps - 1) A.seed_out[0] = lcg_next_seed(t2);
-        }
     }
 
     // ---- write the band back ------------------------------------------------------------------
@@ -288,47 +371,74 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
         *reinterpret_cast<float4 *>(A.out + (size_t)(r0 + k) * L0 + 4 * t) =
             make_float4(phi[k][0], phi[k][1], phi[k][2], phi[k][3]);
     if (myclamp) atomicAdd(A.nclamped, (unsigned long long)myclamp);
-    if (failed) atomicExch(A.error_flag, 1u);
 }
 
-template <int ROWS, int MATH>
-__global__ void __launch_bounds__(256, 1) resident2d_kernel(const ResidentArgs A) {
+template <int ROWS, int MATH, int POT, int TT>
+__global__ void __launch_bounds__(288, 1) resident2d_kernel(const ResidentArgs A) {
     extern __shared__ float smem_f[];
     // an earlier launch flagged an event: this one will be replayed.  (If the flag rises while
     // the grid is still starting, late CTAs leave here and their neighbours' waits give up on it.)
     if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;
     const int b = blockIdx.x, nb = gridDim.x;
+    const int T = TT ? TT : (int)blockDim.x - 32;
     const int r0 = (int)(((long long)b * A.L1) / nb), r1 = (int)(((long long)(b + 1) * A.L1) / nb);
-    if (r1 - r0 == ROWS) resident_run<ROWS, MATH>(A, r0, smem_f);
-    else resident_run<(ROWS > 1 ? ROWS - 1 : 1), MATH>(A, r0, smem_f);
+    float *hbuf = smem_f;                 // [2 buffers][2 (below, above)][L0]
+    float *work = smem_f + 4 * A.L0;
+    if ((int)threadIdx.x >= T) {
+        resident_comm_warp(A, hbuf, r0, r1 - r0, T);
+        return;
+    }
+    if (r1 - r0 == ROWS) resident_run<ROWS, MATH, POT, TT>(A, r0, work, hbuf);
+    else resident_run<(ROWS > 1 ? ROWS - 1 : 1), MATH, POT, TT>(A, r0, work, hbuf);
 }
 
-// history -> running means (tau_kernel.cl:144-145 per time slice), one thread per slice
-__global__ void __launch_bounds__(1024) welford_history_kernel(const WelfordArgs A) {
+// per-step global sums of the history: one warp per step -> step_sums[n] = (sum phi, sum phi^2)
+__global__ void __launch_bounds__(256) history_sums_kernel(const WelfordArgs A, double *step_sums) {
+    if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), l = threadIdx.x & 31;
+    if (n >= A.nsteps) return;
+    double s1 = 0, s2 = 0;
+    for (int k = l; k < A.nt; k += 32) s1 += A.hist_rows[(size_t)n * A.nt + k];
+    for (int k = l; k < A.np2; k += 32) s2 += A.hist_p2[(size_t)n * A.np2 + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (l == 0) {
+        step_sums[2 * n] = s1;
+        step_sums[2 * n + 1] = s2;
+    }
+}
+
+// history -> running means (tau_kernel.cl:144-145 per time slice): one thread per slice walks
+// the steps in order (the recurrence is sequential in the step index, parallel in the slice)
+__global__ void __launch_bounds__(128) welford_history_kernel(const WelfordArgs A, const double *step_sums) {
     if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const double inv_vs = 1.0 / (double)A.vslice;  // vslice is a small integer: P exact enough (<=1 ulp)
     if (t < A.nt) {
         double x = A.slice_x[t], xx0 = A.slice_xx0[t], last = 0;
+#pragma unroll 4
         for (int n = 0; n < A.nsteps; ++n) {
             const double cnt = (double)(A.runs + n + 1);
-            const double P = A.hist_rows[(size_t)n * A.nt + t] / (double)A.vslice;
+            last = A.hist_rows[(size_t)n * A.nt + t];
+            const double P = last / (double)A.vslice;
             const double Pm = A.hist_rows[(size_t)n * A.nt + A.tmid] / (double)A.vslice;
             xx0 = xx0 + (P * Pm - xx0) / cnt;
             x = x + (P - x) / cnt;
-            last = A.hist_rows[(size_t)n * A.nt + t];
         }
         A.slice_x[t] = x;
         A.slice_xx0[t] = xx0;
         A.slice_sum[t] = last;
     }
-    if (t == 0) {
+    (void)inv_vs;
+    if (t == A.nt) {  // one spare thread: running means of <phi>, <phi^2>
         double m1 = A.sums_mean[0], m2 = A.sums_mean[1], s1 = 0, s2 = 0;
         const double vol = (double)A.vslice * (double)A.nt;
         for (int n = 0; n < A.nsteps; ++n) {
-            s1 = 0;
-            s2 = 0;
-            for (int k = 0; k < A.nt; ++k) s1 += A.hist_rows[(size_t)n * A.nt + k];
-            for (int k = 0; k < A.np2; ++k) s2 += A.hist_p2[(size_t)n * A.np2 + k];
+            s1 = step_sums[2 * n];
+            s2 = step_sums[2 * n + 1];
             const double cnt = (double)(A.runs + n + 1);
             m1 += (s1 / vol - m1) / cnt;
             m2 += (s2 / vol - m2) / cnt;
@@ -340,33 +450,44 @@ __global__ void __launch_bounds__(1024) welford_history_kernel(const WelfordArgs
     }
 }
 
-cudaError_t launch_welford_history(const WelfordArgs &A, cudaStream_t stream) {
-    welford_history_kernel<<<(A.nt + 1023) / 1024, 1024, 0, stream>>>(A);
+cudaError_t launch_welford_history(const WelfordArgs &A, double *step_sums, cudaStream_t stream) {
+    history_sums_kernel<<<(A.nsteps + 7) / 8, 256, 0, stream>>>(A, step_sums);
+    welford_history_kernel<<<(A.nt + 1 + 127) / 128, 128, 0, stream>>>(A, step_sums);
     return cudaGetLastError();
 }
 
-template <int ROWS>
+template <int ROWS, int TT>
 static cudaError_t launch_rows(const ResidentArgs &A, int math, int nblocks, int threads, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)2 * ROWS * 2 * threads + (size_t)(ROWS + 1) * threads);
+    const size_t smem = sizeof(float) * ((size_t)4 * A.L0 + (size_t)2 * ROWS * 2 * threads + (size_t)2 * (ROWS + 1) * threads) +
+                        sizeof(uint4) * (size_t)ROWS * threads;
     void *args[] = {(void *)&A};
-    const void *fn = math ? (const void *)resident2d_kernel<ROWS, 1> : (const void *)resident2d_kernel<ROWS, 0>;
+    const void *fn;
+    if (A.pot == 4) fn = math ? (const void *)resident2d_kernel<ROWS, 1, 4, TT> : (const void *)resident2d_kernel<ROWS, 0, 4, TT>;
+    else fn = math ? (const void *)resident2d_kernel<ROWS, 1, 0, TT> : (const void *)resident2d_kernel<ROWS, 0, 0, TT>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaLaunchCooperativeKernel(fn, dim3(nblocks), dim3(threads), args, smem, st);
+    return cudaLaunchCooperativeKernel(fn, dim3(nblocks), dim3(threads + 32), args, smem, st);
 }
 
 // rows_max = ceil(L1 / nblocks)
 cudaError_t launch_resident2d(const ResidentArgs &A, int math, int nblocks, int rows_max, cudaStream_t st) {
     const int threads = A.L0 / 4;
+    if (threads == 256) {  // rows of 1024 sites (configs[1]): fully specialised
+        switch (rows_max) {
+            case 4: return launch_rows<4, 256>(A, math, nblocks, threads, st);
+            case 7: return launch_rows<7, 256>(A, math, nblocks, threads, st);
+            case 8: return launch_rows<8, 256>(A, math, nblocks, threads, st);
+        }
+    }
     switch (rows_max) {
-        case 1: return launch_rows<1>(A, math, nblocks, threads, st);
-        case 2: return launch_rows<2>(A, math, nblocks, threads, st);
-        case 3: return launch_rows<3>(A, math, nblocks, threads, st);
-        case 4: return launch_rows<4>(A, math, nblocks, threads, st);
-        case 5: return launch_rows<5>(A, math, nblocks, threads, st);
-        case 6: return launch_rows<6>(A, math, nblocks, threads, st);
-        case 7: return launch_rows<7>(A, math, nblocks, threads, st);
-        case 8: return launch_rows<8>(A, math, nblocks, threads, st);
+        case 1: return launch_rows<1, 0>(A, math, nblocks, threads, st);
+        case 2: return launch_rows<2, 0>(A, math, nblocks, threads, st);
+        case 3: return launch_rows<3, 0>(A, math, nblocks, threads, st);
+        case 4: return launch_rows<4, 0>(A, math, nblocks, threads, st);
+        case 5: return launch_rows<5, 0>(A, math, nblocks, threads, st);
+        case 6: return launch_rows<6, 0>(A, math, nblocks, threads, st);
+        case 7: return launch_rows<7, 0>(A, math, nblocks, threads, st);
+        case 8: return launch_rows<8, 0>(A, math, nblocks, threads, st);
     }
     return cudaErrorInvalidValue;
 }
