@@ -498,7 +498,8 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     // per-chain couplings live in device arrays for the streaming kernel; the resident kernel is
     // single-chain and takes them by value: keep both in sync through sq_set_chain (host mirror)
     if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
-    CK(launch_resident2d(A, p.math, c->res_nb, c->res_rows, c->stream));
+    static const int strip_w = getenv("SQ_RESIDENT_STRIP") ? atoi(getenv("SQ_RESIDENT_STRIP")) : 0;  // tuning knob
+    CK(launch_resident2d(A, p.math, c->res_nb, c->res_rows, strip_w, c->stream));
     if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
     c->launches++;
     WelfordArgs W{};

@@ -119,7 +119,7 @@ struct ResidentArgs {
     unsigned long long *nclamped;
     unsigned *error_flag;
 };
-cudaError_t launch_resident2d(const ResidentArgs &A, int math, int nblocks, int rows_max, cudaStream_t st);
+cudaError_t launch_resident2d(const ResidentArgs &A, int math, int nblocks, int rows_max, int strip_w, cudaStream_t st);
 
 struct WelfordArgs {
     int nt, nsteps, tmid, np2;

@@ -43,8 +43,8 @@ __device__ __forceinline__ float4 ld_cg_f4(const float *p) {
 }
 
 // cold path: exact event test of the 4 draws of a strip (literal replay is the host's job)
-__device__ __noinline__ void strip_events_cold(u64 *event_key_ptr, int step, u64 sm, u64 g0) {
-    for (int e = 0; e < 4; ++e) {
+__device__ __noinline__ void strip_events_cold(u64 *event_key_ptr, int step, u64 sm, u64 g0, int w) {
+    for (int e = 0; e < w; ++e) {
         u64 t1, t2;
         lcg_draw(sm, g0 + e, t1, t2);
         if (lcg_event(sm, t1, t2)) atomicMin((unsigned long long *)event_key_ptr, event_key(step, 0, g0 + e));
@@ -83,10 +83,6 @@ __device__ __forceinline__ float site_update(float phi, float nsum, unsigned u1,
 
 }  // namespace
 
-// named barriers (id 0 is __syncthreads and is not used once the roles split)
-constexpr int BAR_EDGES = 1;   // compute warps only: shared-memory edges / row sums handed over
-constexpr int BAR_CONSUMED = 2; // compute arrive, comm warp sync: this step's staged rows have been read
-constexpr int BAR_HALO = 3;    // comm warp arrive, compute sync: neighbours' rows are in shared memory
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
@@ -105,100 +101,29 @@ __device__ __forceinline__ unsigned long long ll_pack(float v, unsigned tag) {
     return ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
 }
 
-// ---- the communication warp: receive the neighbours' boundary rows (flag-in-data), stage them ---
 // Halo protocol: every boundary value travels as one 64-bit word {float, step tag}.  A word whose
 // tag equals the expected step IS the data of that step (64-bit scalar accesses are single-copy
 // atomic), so the producer needs no fence and no separate flag, the consumer no acquire:
 // one L2 write + one L2 read of latency.  Tags never repeat within a context (step0 is monotonic,
-// also across replayed launches).
-__device__ __forceinline__ void resident_comm_warp(const ResidentArgs &A, float *hbuf, int r0, int nr, int T) {
-    const int lane = threadIdx.x & 31, b = blockIdx.x, nb = gridDim.x, L0 = A.L0;
-    const int bup = (b + 1 == nb) ? 0 : b + 1, bdn = (b == 0) ? nb - 1 : b - 1;
-    const int nall = T + 32;
-    // prologue: halo rows of the initial field, straight from the input buffer
-    {
-        const int rup = (r0 + nr == A.L1) ? 0 : r0 + nr, rdn = (r0 == 0) ? A.L1 - 1 : r0 - 1;
-        for (int i = lane * 4; i < L0; i += 128) {
-            *reinterpret_cast<float4 *>(hbuf + i) = *reinterpret_cast<const float4 *>(A.in + (size_t)rdn * L0 + i);
-            *reinterpret_cast<float4 *>(hbuf + L0 + i) = *reinterpret_cast<const float4 *>(A.in + (size_t)rup * L0 + i);
-        }
-        __threadfence_block();
-        bar_arrive(BAR_HALO, nall);
-    }
-    Seed32 Som = seed_split(A.seed_in[0]);
-    unsigned failed = 0;
-    for (int n = 0; n < A.nsteps; ++n) {
-        if (n + 1 < A.nsteps) {
-            const unsigned want = A.step0 + (unsigned)n + 1u;
-            const unsigned long long *hb = A.halo_ll + (size_t)((n + 1) & 1) * nb * 2 * L0;
-            const unsigned long long *src_dn = hb + ((size_t)bdn * 2 + 1) * L0;  // neighbour below: its LAST row
-            const unsigned long long *src_up = hb + ((size_t)bup * 2 + 0) * L0;  // neighbour above: its FIRST row
-            // lane handles pairs of sites i, i+1 with i = j*64 + lane*2  (L0 <= 1024: j < 16)
-            ulonglong2 d[16], u[16];
-            unsigned pending = 0xFFFFFFFFu, spins = 0;
-            while (pending) {
-                unsigned still = 0;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int i = j * 64 + lane * 2;
-                    if (i < L0 && (pending & (1u << j))) d[j] = ld_relaxed_ll(src_dn + i);
-                    if (i < L0 && (pending & (0x10000u << j))) u[j] = ld_relaxed_ll(src_up + i);
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int i = j * 64 + lane * 2;
-                    if (i < L0) {
-                        if ((unsigned)(d[j].x >> 32) != want || (unsigned)(d[j].y >> 32) != want) still |= 1u << j;
-                        if ((unsigned)(u[j].x >> 32) != want || (unsigned)(u[j].y >> 32) != want) still |= 0x10000u << j;
-                    }
-                }
-                pending = still;
-                if (pending) {
-                    ++spins;
-                    // the launch is being abandoned (an RNG event must be replayed): stop waiting
-                    if ((spins & 15u) == 0 && *((volatile const u64 *)A.event_key) != NO_EVENT) break;
-                    if (spins > (1u << 20)) { failed = 1; break; }  // never hang the GPU
-                }
-            }
-            // the compute warps have finished reading the buffer we are about to overwrite
-            bar_sync(BAR_CONSUMED, nall);
-            float *dst = hbuf + (size_t)((n + 1) & 1) * 2 * L0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int i = j * 64 + lane * 2;
-                if (i < L0) {
-                    *reinterpret_cast<float2 *>(dst + i) =
-                        make_float2(__uint_as_float((unsigned)d[j].x), __uint_as_float((unsigned)d[j].y));
-                    *reinterpret_cast<float2 *>(dst + L0 + i) =
-                        make_float2(__uint_as_float((unsigned)u[j].x), __uint_as_float((unsigned)u[j].y));
-                }
-            }
-            __threadfence_block();
-            bar_arrive(BAR_HALO, nall);
-        }
-        // the omega work-item's draw (gid = V), tau_kernel.cl:103-110
-        if (b == 0 && lane == 0) {
-            const u64 S = seed_join(Som);
-            const u64 sV = lcg_apply(A.vol_jump, S, 0) & LCG_MASK;
-            u64 t1, t2;
-            lcg_draw(sV, (u64)A.V, t1, t2);
-            if (lcg_event(sV, t1, t2))
-                atomicMin((unsigned long long *)A.event_key, event_key(A.step_index0 + n, 0, (u64)A.V));
-            Som = seed_split(lcg_next_seed(t2));
-            if (n == A.nsteps - 1) A.seed_out[0] = lcg_next_seed(t2);
-        }
-    }
-    if (__any_sync(0xffffffffu, failed) && lane == 0) atomicExch(A.error_flag, 1u);
-}
+// also across replayed launches).  Each thread prefetches the words above/below its own columns
+// into registers in the middle of a step (non-blocking) and only checks the tags when it needs
+// the values at the start of the next step; a miss re-polls (bounded, abort-aware).
 
 // ---- compute warps.  NR = rows owned by this CTA (compile-time: the band stays in registers) ---
+// W  = sites per thread and row (4: 128-bit strips, 8 warps per 1024-site row; 2: 16 warps -- more
+//      thread-level parallelism for the dependent integer/SFU chains, the kernel's real limiter)
 // TT = compile-time threads per row (0: runtime) so shared-memory offsets become immediates.
-template <int NR, int MATH, int POT, int TT>
-__device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, float *smem, float *hbuf) {
-    const int T = TT ? TT : (int)blockDim.x - 32;
+template <int W>
+struct alignas(4 * W) RowPack {
+    float v[W];
+};
+
+template <int NR, int MATH, int POT, int W, int TT>
+__device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, float *smem) {
+    const int T = TT ? TT : (int)blockDim.x;
     const int t = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
     const int L0 = A.L0;
-    const int nall = T + 32;
+    const int bup = (b + 1 == nb) ? 0 : b + 1, bdn = (b == 0) ? nb - 1 : b - 1;
     // shared: edges [2 buffers][NR rows][2 (first,last)][T] ; row-sum transpose [2][NR+1][T] ;
     // per-strip chain state [NR][T] x {seed lo, seed hi, K lo, K hi} (kept out of the register file)
     float *edge = smem;
@@ -215,14 +140,15 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
     C.k2 = (float)(2.0 * 0.6931471805599453 * A.nscale * A.nscale);
 
     // ---- load the band, set up the per-strip chain state -----------------------------------
-    float phi[NR][4];
+    float phi[NR][W];
     const u64 S0 = A.seed_in[0];
     const u64 S1 = (A.P * S0 + A.Q) & LCG_MASK;  // predicted seed after one whole step
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
-        const float4 v = *reinterpret_cast<const float4 *>(A.in + (size_t)(r0 + k) * L0 + 4 * t);
-        phi[k][0] = v.x; phi[k][1] = v.y; phi[k][2] = v.z; phi[k][3] = v.w;
-        const u64 g = (u64)(r0 + k) * L0 + 4 * t;
+        const RowPack<W> v = *reinterpret_cast<const RowPack<W> *>(A.in + (size_t)(r0 + k) * L0 + W * t);
+#pragma unroll
+        for (int e = 0; e < W; ++e) phi[k][e] = v.v[e];
+        const u64 g = (u64)(r0 + k) * L0 + W * t;
         const u64 s0 = lcg_seed_at(S0, 0, g, A.jump);
         const u64 s1 = lcg_seed_at(S1, 0, g, A.jump);
         const u64 K = (s1 - A.P * s0) & LCG_MASK;
@@ -231,16 +157,29 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
     const unsigned Pl = (unsigned)A.P, Ph = (unsigned)(A.P >> 32);
     // c = gid*A + B of the first site of row 0's strip; rows advance it by L0*A
     unsigned c0l, c0h;
-    site_const((u64)r0 * L0 + 4 * t, c0l, c0h);
+    site_const((u64)r0 * L0 + W * t, c0l, c0h);
     const u64 rowA = (u64)L0 * LCG_A;
 
     // edges of the initial field
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
         edge[((0 * NR + k) * 2 + 0) * T + t] = phi[k][0];
-        edge[((0 * NR + k) * 2 + 1) * T + t] = phi[k][3];
+        edge[((0 * NR + k) * 2 + 1) * T + t] = phi[k][W - 1];
     }
-    bar_sync(BAR_EDGES, T);
+    __syncthreads();
+
+    // neighbours' rows of the initial field, straight from the input buffer
+    float hdn[W], hup[W];
+    {
+        const int rup = (r0 + NR == A.L1) ? 0 : r0 + NR, rdn = (r0 == 0) ? A.L1 - 1 : r0 - 1;
+        const RowPack<W> d = *reinterpret_cast<const RowPack<W> *>(A.in + (size_t)rdn * L0 + W * t);
+        const RowPack<W> u = *reinterpret_cast<const RowPack<W> *>(A.in + (size_t)rup * L0 + W * t);
+#pragma unroll
+        for (int e = 0; e < W; ++e) { hdn[e] = d.v[e]; hup[e] = u.v[e]; }
+    }
+    ulonglong2 pre_dn[W / 2], pre_up[W / 2];  // prefetched {value, tag} words of the next step's halo
+    Seed32 Som = seed_split(S0);              // (b==0, t==0): the step-start seed, for the omega draw
+    unsigned failed = 0;
 
     const int tl = (t == 0) ? T - 1 : t - 1, tr = (t + 1 == T) ? 0 : t + 1;
     unsigned myclamp = 0;
@@ -262,79 +201,117 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
             const uint4 st = chain[k * T + t];
             Seed32 s{st.x, st.y};
             const Seed32 s_before = s;
-            float a = 0.f;
+            float a = 0.f, amax = 0.f;
             bool maybe = false;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < W; ++e) {
                 unsigned u1, u2;
                 site_draw(s, cl, ch, u1, u2);
                 site_const_next(cl, ch);
                 maybe |= site_maybe_event(u1, u2);
                 const float p = cur[e];
-                const float xp = (e < 3) ? cur[(e + 1) & 3] : right;
-                const float xm = (e > 0) ? cur[(e + 3) & 3] : left;
+                const float xp = (e < W - 1) ? cur[(e + 1) % W] : right;
+                const float xm = (e > 0) ? cur[(e + W - 1) % W] : left;
                 const float nsum = __fadd_rn(__fadd_rn(__fadd_rn(xp, xm), up[e]), dn[e]);
                 out[e] = site_update<MATH, POT>(p, nsum, u1, u2, C);
                 a = __fadd_rn(a, p);
                 p2 = __fmaf_rn(p, p, p2);
+                amax = fmaxf(amax, fabsf(out[e]));
             }
             // clamp hits (tau_kernel.cl:122-132) are counted on a cold path
-            if (__builtin_expect(fmaxf(fmaxf(fabsf(out[0]), fabsf(out[1])), fmaxf(fabsf(out[2]), fabsf(out[3]))) >= 1000.0f, 0)) {
+            if (__builtin_expect(amax >= 1000.0f, 0)) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) myclamp += (fabsf(out[e]) >= 1000.0f) ? 1u : 0u;
+                for (int e = 0; e < W; ++e) myclamp += (fabsf(out[e]) >= 1000.0f) ? 1u : 0u;
             }
             rs[k * T + t] = a;
             if (__builtin_expect(maybe, 0))
-                strip_events_cold(A.event_key, A.step_index0 + n, seed_join(s_before), (u64)(r0 + k) * L0 + 4 * t);
+                strip_events_cold(A.event_key, A.step_index0 + n, seed_join(s_before), (u64)(r0 + k) * L0 + W * t, W);
             // the strip keeps its gids: next step's seed by one affine map (5 integer ops)
             const u64 p = (u64)st.x * Pl + (((u64)st.w << 32) | st.z);
             const unsigned nh = (unsigned)(p >> 32) + st.x * Ph + st.y * Pl;
             *reinterpret_cast<uint2 *>(&chain[k * T + t]) = make_uint2((unsigned)p, nh);
         };
 
-        // ---- neighbours' rows of the current field, staged by the comm warp ------------------
-        bar_sync(BAR_HALO, nall);
-        float hdn[4], hup[4];
-        {
-            const float4 d = *reinterpret_cast<const float4 *>(hbuf + (size_t)eb * 2 * L0 + 4 * t);
-            const float4 u = *reinterpret_cast<const float4 *>(hbuf + (size_t)eb * 2 * L0 + L0 + 4 * t);
-            hdn[0] = d.x; hdn[1] = d.y; hdn[2] = d.z; hdn[3] = d.w;
-            hup[0] = u.x; hup[1] = u.y; hup[2] = u.z; hup[3] = u.w;
+        // ---- neighbours' rows of the current field: the words prefetched during the last step ---
+        if (n > 0) {
+            const unsigned want = A.step0 + (unsigned)n;
+            const unsigned long long *hb = A.halo_ll + (size_t)eb * nb * 2 * L0 + W * t;
+            const unsigned long long *src_dn = hb + ((size_t)bdn * 2 + 1) * L0;  // neighbour below: its LAST row
+            const unsigned long long *src_up = hb + ((size_t)bup * 2 + 0) * L0;  // neighbour above: its FIRST row
+            unsigned spins = 0;
+            for (;;) {
+                bool ok = true;
+#pragma unroll
+                for (int j = 0; j < W / 2; ++j)
+                    ok &= ((unsigned)(pre_dn[j].x >> 32) == want) & ((unsigned)(pre_dn[j].y >> 32) == want) &
+                          ((unsigned)(pre_up[j].x >> 32) == want) & ((unsigned)(pre_up[j].y >> 32) == want);
+                if (__builtin_expect(ok, 1)) break;
+                ++spins;
+                // the launch is being abandoned (an RNG event must be replayed): stop waiting
+                if ((spins & 15u) == 0 && *((volatile const u64 *)A.event_key) != NO_EVENT) break;
+                if (spins > (1u << 20)) { failed = 1; break; }  // never hang the GPU
+#pragma unroll
+                for (int j = 0; j < W / 2; ++j) {
+                    pre_dn[j] = ld_relaxed_ll(src_dn + 2 * j);
+                    pre_up[j] = ld_relaxed_ll(src_up + 2 * j);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < W / 2; ++j) {
+                hdn[2 * j] = __uint_as_float((unsigned)pre_dn[j].x);
+                hdn[2 * j + 1] = __uint_as_float((unsigned)pre_dn[j].y);
+                hup[2 * j] = __uint_as_float((unsigned)pre_up[j].x);
+                hup[2 * j + 1] = __uint_as_float((unsigned)pre_up[j].y);
+            }
         }
-        if (n + 1 < A.nsteps) bar_arrive(BAR_CONSUMED, nall);
 
         // ---- phase A: the two boundary rows first, publish them (fire and forget) -----------
-        float first[4], last[4];
+        float first[W], last[W];
         if (NR == 1) {
             do_row(0, phi[0], hup, hdn, first);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) last[e] = first[e];
+            for (int e = 0; e < W; ++e) last[e] = first[e];
         } else {
             do_row(0, phi[0], phi[1], hdn, first);
             do_row(NR - 1, phi[NR - 1], hup, phi[NR - 2], last);
         }
-        if (n + 1 < A.nsteps) {  // {value, tag} words: no fence, no flag (see resident_comm_warp)
+        if (n + 1 < A.nsteps) {  // {value, tag} words: no fence, no flag
             const unsigned tag = A.step0 + (unsigned)n + 1u;
-            unsigned long long *ho = A.halo_ll + ((size_t)((n + 1) & 1) * nb + b) * 2 * L0 + 4 * t;
-            *reinterpret_cast<ulonglong2 *>(ho) = make_ulonglong2(ll_pack(first[0], tag), ll_pack(first[1], tag));
-            *reinterpret_cast<ulonglong2 *>(ho + 2) = make_ulonglong2(ll_pack(first[2], tag), ll_pack(first[3], tag));
-            *reinterpret_cast<ulonglong2 *>(ho + L0) = make_ulonglong2(ll_pack(last[0], tag), ll_pack(last[1], tag));
-            *reinterpret_cast<ulonglong2 *>(ho + L0 + 2) = make_ulonglong2(ll_pack(last[2], tag), ll_pack(last[3], tag));
+            unsigned long long *ho = A.halo_ll + ((size_t)((n + 1) & 1) * nb + b) * 2 * L0 + W * t;
+#pragma unroll
+            for (int e = 0; e < W; e += 2) {
+                *reinterpret_cast<ulonglong2 *>(ho + e) = make_ulonglong2(ll_pack(first[e], tag), ll_pack(first[e + 1], tag));
+                *reinterpret_cast<ulonglong2 *>(ho + L0 + e) = make_ulonglong2(ll_pack(last[e], tag), ll_pack(last[e + 1], tag));
+            }
         }
 
         // ---- phase B: interior rows, in place (old copies of the rows still needed below) ----
-        float prev[4];  // old values of row k-1
+        // after interior row KPRE: issue (do not wait for) the loads of the neighbours' new rows
+        constexpr int KPRE = (NR >= 5) ? NR - 4 : ((NR >= 3) ? 1 : 0);
+        auto prefetch_halo = [&]() {
+            if (n + 1 < A.nsteps) {
+                const unsigned long long *hb = A.halo_ll + (size_t)(eb ^ 1) * nb * 2 * L0 + W * t;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) prev[e] = phi[0][e];
+                for (int j = 0; j < W / 2; ++j) {
+                    pre_dn[j] = ld_relaxed_ll(hb + ((size_t)bdn * 2 + 1) * L0 + 2 * j);
+                    pre_up[j] = ld_relaxed_ll(hb + ((size_t)bup * 2 + 0) * L0 + 2 * j);
+                }
+            }
+        };
+        float prev[W];  // old values of row k-1
+#pragma unroll
+        for (int e = 0; e < W; ++e) prev[e] = phi[0][e];
 #pragma unroll
         for (int k = 1; k < NR - 1; ++k) {
-            float out[4];
+            float out[W];
             do_row(k, phi[k], phi[k + 1], prev, out);  // phi[k+1] is still old (row NR-1 lives in `last`)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { prev[e] = phi[k][e]; phi[k][e] = out[e]; }
+            for (int e = 0; e < W; ++e) { prev[e] = phi[k][e]; phi[k][e] = out[e]; }
+            if (k == KPRE) prefetch_halo();
         }
+        if (KPRE < 1) prefetch_halo();
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
+        for (int e = 0; e < W; ++e) {
             phi[0][e] = first[e];
             if (NR > 1) phi[NR - 1][e] = last[e];
         }
@@ -344,10 +321,10 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
 #pragma unroll
         for (int k = 0; k < NR; ++k) {
             edge[((nbuf * NR + k) * 2 + 0) * T + t] = phi[k][0];
-            edge[((nbuf * NR + k) * 2 + 1) * T + t] = phi[k][3];
+            edge[((nbuf * NR + k) * 2 + 1) * T + t] = phi[k][W - 1];
         }
         rs[NR * T + t] = p2;
-        bar_sync(BAR_EDGES, T);
+        __syncthreads();
 
         // ---- per-row sums: warp w reduces row w (and the phi^2 column) ---------------------
         {
@@ -363,33 +340,42 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
                 }
             }
         }
+
+        // ---- the omega work-item's draw (gid = V), tau_kernel.cl:103-110 ----------------------
+        if (b == 0 && t == 0) {
+            const u64 S = seed_join(Som);
+            const u64 sV = lcg_apply(A.vol_jump, S, 0) & LCG_MASK;
+            u64 t1, t2;
+            lcg_draw(sV, (u64)A.V, t1, t2);
+            if (lcg_event(sV, t1, t2))
+                atomicMin((unsigned long long *)A.event_key, event_key(A.step_index0 + n, 0, (u64)A.V));
+            Som = seed_split(lcg_next_seed(t2));
+            if (n == A.nsteps - 1) A.seed_out[0] = lcg_next_seed(t2);
+        }
     }
 
     // ---- write the band back ------------------------------------------------------------------
 #pragma unroll
-    for (int k = 0; k < NR; ++k)
-        *reinterpret_cast<float4 *>(A.out + (size_t)(r0 + k) * L0 + 4 * t) =
-            make_float4(phi[k][0], phi[k][1], phi[k][2], phi[k][3]);
+    for (int k = 0; k < NR; ++k) {
+        RowPack<W> v;
+#pragma unroll
+        for (int e = 0; e < W; ++e) v.v[e] = phi[k][e];
+        *reinterpret_cast<RowPack<W> *>(A.out + (size_t)(r0 + k) * L0 + W * t) = v;
+    }
     if (myclamp) atomicAdd(A.nclamped, (unsigned long long)myclamp);
+    if (failed) atomicExch(A.error_flag, 1u);
 }
 
-template <int ROWS, int MATH, int POT, int TT>
-__global__ void __launch_bounds__(288, 1) resident2d_kernel(const ResidentArgs A) {
+template <int ROWS, int MATH, int POT, int W, int TT>
+__global__ void __launch_bounds__(W == 2 ? 512 : 256, 1) resident2d_kernel(const ResidentArgs A) {
     extern __shared__ float smem_f[];
     // an earlier launch flagged an event: this one will be replayed.  (If the flag rises while
     // the grid is still starting, late CTAs leave here and their neighbours' waits give up on it.)
     if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;
     const int b = blockIdx.x, nb = gridDim.x;
-    const int T = TT ? TT : (int)blockDim.x - 32;
     const int r0 = (int)(((long long)b * A.L1) / nb), r1 = (int)(((long long)(b + 1) * A.L1) / nb);
-    float *hbuf = smem_f;                 // [2 buffers][2 (below, above)][L0]
-    float *work = smem_f + 4 * A.L0;
-    if ((int)threadIdx.x >= T) {
-        resident_comm_warp(A, hbuf, r0, r1 - r0, T);
-        return;
-    }
-    if (r1 - r0 == ROWS) resident_run<ROWS, MATH, POT, TT>(A, r0, work, hbuf);
-    else resident_run<(ROWS > 1 ? ROWS - 1 : 1), MATH, POT, TT>(A, r0, work, hbuf);
+    if (r1 - r0 == ROWS) resident_run<ROWS, MATH, POT, W, TT>(A, r0, smem_f);
+    else resident_run<(ROWS > 1 ? ROWS - 1 : 1), MATH, POT, W, TT>(A, r0, smem_f);
 }
 
 // per-step global sums of the history: one warp per step -> step_sums[n] = (sum phi, sum phi^2)
@@ -456,38 +442,46 @@ cudaError_t launch_welford_history(const WelfordArgs &A, double *step_sums, cuda
     return cudaGetLastError();
 }
 
-template <int ROWS, int TT>
-static cudaError_t launch_rows(const ResidentArgs &A, int math, int nblocks, int threads, cudaStream_t st) {
-    const size_t smem = sizeof(float) * ((size_t)4 * A.L0 + (size_t)2 * ROWS * 2 * threads + (size_t)2 * (ROWS + 1) * threads) +
+template <int ROWS, int W, int TT>
+static cudaError_t launch_rows(const ResidentArgs &A, int math, int nblocks, cudaStream_t st) {
+    const int threads = A.L0 / W;
+    const size_t smem = sizeof(float) * ((size_t)2 * ROWS * 2 * threads + (size_t)2 * (ROWS + 1) * threads) +
                         sizeof(uint4) * (size_t)ROWS * threads;
     void *args[] = {(void *)&A};
     const void *fn;
-    if (A.pot == 4) fn = math ? (const void *)resident2d_kernel<ROWS, 1, 4, TT> : (const void *)resident2d_kernel<ROWS, 0, 4, TT>;
-    else fn = math ? (const void *)resident2d_kernel<ROWS, 1, 0, TT> : (const void *)resident2d_kernel<ROWS, 0, 0, TT>;
+    if (A.pot == 4) fn = math ? (const void *)resident2d_kernel<ROWS, 1, 4, W, TT> : (const void *)resident2d_kernel<ROWS, 0, 4, W, TT>;
+    else fn = math ? (const void *)resident2d_kernel<ROWS, 1, 0, W, TT> : (const void *)resident2d_kernel<ROWS, 0, 0, W, TT>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaLaunchCooperativeKernel(fn, dim3(nblocks), dim3(threads + 32), args, smem, st);
+    return cudaLaunchCooperativeKernel(fn, dim3(nblocks), dim3(threads), args, smem, st);
 }
 
-// rows_max = ceil(L1 / nblocks)
-cudaError_t launch_resident2d(const ResidentArgs &A, int math, int nblocks, int rows_max, cudaStream_t st) {
-    const int threads = A.L0 / 4;
-    if (threads == 256) {  // rows of 1024 sites (configs[1]): fully specialised
-        switch (rows_max) {
-            case 4: return launch_rows<4, 256>(A, math, nblocks, threads, st);
-            case 7: return launch_rows<7, 256>(A, math, nblocks, threads, st);
-            case 8: return launch_rows<8, 256>(A, math, nblocks, threads, st);
+// rows_max = ceil(L1 / nblocks).  strip_w: 2 or 4 sites per thread and row (0 = default).
+cudaError_t launch_resident2d(const ResidentArgs &A, int math, int nblocks, int rows_max, int strip_w, cudaStream_t st) {
+    if (A.L0 == 1024) {  // rows of 1024 sites (configs[1]): fully specialised
+        if (strip_w != 4) {
+            switch (rows_max) {
+                case 4: return launch_rows<4, 2, 512>(A, math, nblocks, st);
+                case 7: return launch_rows<7, 2, 512>(A, math, nblocks, st);
+                case 8: return launch_rows<8, 2, 512>(A, math, nblocks, st);
+            }
+        } else {
+            switch (rows_max) {
+                case 4: return launch_rows<4, 4, 256>(A, math, nblocks, st);
+                case 7: return launch_rows<7, 4, 256>(A, math, nblocks, st);
+                case 8: return launch_rows<8, 4, 256>(A, math, nblocks, st);
+            }
         }
     }
     switch (rows_max) {
-        case 1: return launch_rows<1, 0>(A, math, nblocks, threads, st);
-        case 2: return launch_rows<2, 0>(A, math, nblocks, threads, st);
-        case 3: return launch_rows<3, 0>(A, math, nblocks, threads, st);
-        case 4: return launch_rows<4, 0>(A, math, nblocks, threads, st);
-        case 5: return launch_rows<5, 0>(A, math, nblocks, threads, st);
-        case 6: return launch_rows<6, 0>(A, math, nblocks, threads, st);
-        case 7: return launch_rows<7, 0>(A, math, nblocks, threads, st);
-        case 8: return launch_rows<8, 0>(A, math, nblocks, threads, st);
+        case 1: return launch_rows<1, 4, 0>(A, math, nblocks, st);
+        case 2: return launch_rows<2, 4, 0>(A, math, nblocks, st);
+        case 3: return launch_rows<3, 4, 0>(A, math, nblocks, st);
+        case 4: return launch_rows<4, 4, 0>(A, math, nblocks, st);
+        case 5: return launch_rows<5, 4, 0>(A, math, nblocks, st);
+        case 6: return launch_rows<6, 4, 0>(A, math, nblocks, st);
+        case 7: return launch_rows<7, 4, 0>(A, math, nblocks, st);
+        case 8: return launch_rows<8, 4, 0>(A, math, nblocks, st);
     }
     return cudaErrorInvalidValue;
 }
