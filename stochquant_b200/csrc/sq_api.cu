@@ -56,6 +56,7 @@ struct sq_ctx {
     u64 *l_seeds[2] = {nullptr, nullptr};
     u64 *l_event = nullptr;
     RebaseEntry *l_rebase = nullptr;
+    JumpEntry *l_slice_jump = nullptr, *l_strip_jump = nullptr;
     double *l_partials = nullptr, *l_slice_sum = nullptr, *l_slice_x = nullptr, *l_slice_xx0 = nullptr,
            *l_sums = nullptr, *l_sums_mean = nullptr, *l_m2 = nullptr, *l_lam = nullptr, *l_redbuf = nullptr;
     unsigned long long *l_nclamped = nullptr;
@@ -165,7 +166,7 @@ extern "C" void sq_free(sq_ctx *c) {
                     c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps,
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
-                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped,
+                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_slice_jump, c->l_strip_jump,
                     c->r_halo, c->r_error, c->r_hist_rows, c->r_hist_p2, c->r_step_sums};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -272,6 +273,15 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
     if ((rc = dalloc(&c->l_lam, (size_t)p.nchains))) return rc;
     if ((rc = dalloc(&c->l_redbuf, 2 * 1024))) return rc;
     if ((rc = dalloc(&c->l_nclamped, 1))) return rc;
+    {  // jump coefficients that do not depend on the seed: slice starts and first strips
+        std::vector<JumpEntry> sj((size_t)c->nt), qj((size_t)256 * c->ctas_per_slice);
+        for (int t = 0; t < c->nt; ++t) sj[t] = jump_entry((u64)(p.slab_t0 + t) * (u64)c->vslice);
+        for (size_t q = 0; q < qj.size(); ++q) qj[q] = jump_entry((u64)q * (u64)vec);
+        CK(cudaMalloc((void **)&c->l_slice_jump, sizeof(JumpEntry) * sj.size()));
+        CK(cudaMalloc((void **)&c->l_strip_jump, sizeof(JumpEntry) * qj.size()));
+        CK(cudaMemcpy(c->l_slice_jump, sj.data(), sizeof(JumpEntry) * sj.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->l_strip_jump, qj.data(), sizeof(JumpEntry) * qj.size(), cudaMemcpyHostToDevice));
+    }
     std::vector<u64> seeds((size_t)p.nchains);
     std::vector<double> m2((size_t)p.nchains, p.m2), lam((size_t)p.nchains, p.lambda);
     for (int k = 0; k < p.nchains; ++k) seeds[k] = seed + (u64)k;
@@ -413,6 +423,9 @@ static LatticeArgs lattice_args(sq_ctx *c, double dtau, int k /* step in sequenc
     A.lam_chain = c->l_lam;
     A.seed_in = c->l_seeds[b];
     A.seed_out = c->l_seeds[b ^ 1];
+    A.k2_f = (float)(2.0 * 0.6931471805599453 * A.nscale * A.nscale);
+    A.slice_jump = c->l_slice_jump;
+    A.strip_jump = c->l_strip_jump;
     A.stride_jump = jump_entry((u64)A.strips_per_cta_iter * (u64)vec);
     A.vol_jump = jump_entry((u64)c->V);
     A.jump = c->d_jump;
@@ -483,6 +496,12 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     A.nscale = L.nscale;
     A.m2 = p.m2;
     A.lam = p.lambda;
+    A.c_lap_f = (float)A.c_lap;
+    A.c_dt_f = (float)A.c_dt;
+    A.c_2dt_f = 2.0f * A.c_dt_f;
+    A.m2_f = (float)A.m2;
+    A.lam_f = (float)A.lam;
+    A.k2_f = (float)(2.0 * 0.6931471805599453 * A.nscale * A.nscale);
     A.seed_in = c->l_seeds[c->cur];
     A.seed_out = c->l_seeds[c->cur ^ 1];
     const JumpEntry e = jump_entry((u64)c->V + 1);

@@ -69,6 +69,9 @@ struct LatticeArgs {
     const double *m2_chain, *lam_chain;
     const u64 *seed_in;  // [nchains] full-u64 seed at step start
     u64 *seed_out;       // [nchains] seed after the step's V+1 draws
+    float k2_f;              // 2 ln2 nscale^2 (FAST noise amplitude folded under the square root)
+    const JumpEntry *slice_jump;  // [nt]   jump from gid 0 to the start of local slice t
+    const JumpEntry *strip_jump;  // [strips_per_cta_iter] jump over q*VEC draws (first strip of a thread)
     JumpEntry stride_jump;   // jump over strips_per_cta_iter*VEC draws
     JumpEntry vol_jump;      // jump over V draws from gid 0 (to the omega draw)
     const JumpEntry *jump;
@@ -108,6 +111,7 @@ struct ResidentArgs {
     float *out;
     unsigned long long *halo_ll;  // [2][nblocks][2][L0] words {float bits, step tag}
     double c_lap, c_dt, nscale, m2, lam;
+    float c_lap_f, c_dt_f, c_2dt_f, m2_f, lam_f, k2_f;  // host-side casts of the above (+ 2 ln2 nscale^2)
     const u64 *seed_in;
     u64 *seed_out;
     u64 P, Q;            // whole-step affine seed advance over V+1 draws

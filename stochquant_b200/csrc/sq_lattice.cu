@@ -17,7 +17,7 @@
 //   * per-slice sum(phi), sum(phi^2): registers -> warp shuffle -> one fp64 partial per
 //     CTA, reduced in fixed order by finalize_kernel (bit-reproducible, no float atomics).
 #include "sq_kernels.h"
-#include "sq_noise.cuh"
+#include "sq_site.cuh"
 
 namespace sq {
 
@@ -60,6 +60,16 @@ __device__ __forceinline__ void rebase_lookup(const LatticeArgs &A, int chain, u
     }
 }
 
+// cold paths, arguments by value (taking the address of a register array would spill it)
+__device__ __noinline__ void strip_events_cold(u64 *event_key_ptr, int step, int chain, u64 sm, u64 g0, int w) {
+    for (int e = 0; e < w; ++e) {
+        u64 t1, t2;
+        lcg_draw(sm, g0 + e, t1, t2);
+        if (lcg_event(sm, t1, t2)) atomicMin((unsigned long long *)event_key_ptr, event_key(step, chain, g0 + e));
+        sm = lcg_next_seed(t2) & LCG_MASK;
+    }
+}
+
 }  // namespace
 
 template <typename real, int MATH, int NDIM, bool REBASE>
@@ -82,7 +92,8 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
     const real c_lap = (real)A.c_lap, c_dt = (real)A.c_dt;
     const real m2 = (real)(A.m2_chain ? A.m2_chain[chain] : A.m2);
     const real lam = (real)(A.lam_chain ? A.lam_chain[chain] : A.lam);
-    const float nscale_f = (float)A.nscale;
+    const real c_2dt = (real)2 * c_dt;
+    const float k2_f = A.k2_f;
     const unsigned L0 = (unsigned)A.dim[0];
     const unsigned L1 = (NDIM >= 3) ? (unsigned)A.dim[1] : 1u;
     const unsigned L2 = (NDIM >= 4) ? (unsigned)A.dim[2] : 1u;
@@ -103,7 +114,9 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
             rebase_lookup(A, chain, S, g0, bg, bs);
             s = lcg_seed_at(bs, bg, g0 - bg, A.jump);
         } else if (first) {
-            s = lcg_seed_at(S, 0, g0, A.jump);
+            // two precomputed jumps: to the slice start, then to this thread's first strip
+            const u64 ss = lcg_apply(A.slice_jump[tl], S, 0) & LCG_MASK;
+            s = lcg_apply(A.strip_jump[q], ss, gslice) & LCG_MASK;
         } else {
             s = lcg_apply(A.stride_jump, s_prev, g_prev) & LCG_MASK;
         }
@@ -117,85 +130,91 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
         const Pack<real> c = *reinterpret_cast<const Pack<real> *>(cur + off);
         const Pack<real> pm = *reinterpret_cast<const Pack<real> *>(tm + off);
         const Pack<real> pp = *reinterpret_cast<const Pack<real> *>(tp + off);
-        Pack<real> u1, d1, u2, d2;
+        Pack<real> u1p, d1p, u2p, d2p;
         if (NDIM >= 3) {
             const unsigned x1 = (NDIM >= 4) ? rest % L1 : rest;
             const long long up = (x1 + 1 == L1) ? -(long long)(L1 - 1) * L0 : (long long)L0;
             const long long dn = (x1 == 0) ? (long long)(L1 - 1) * L0 : -(long long)L0;
-            u1 = *reinterpret_cast<const Pack<real> *>(cur + off + up);
-            d1 = *reinterpret_cast<const Pack<real> *>(cur + off + dn);
+            u1p = *reinterpret_cast<const Pack<real> *>(cur + off + up);
+            d1p = *reinterpret_cast<const Pack<real> *>(cur + off + dn);
         }
         if (NDIM >= 4) {
             const unsigned x2 = rest / L1;
             const long long st2 = (long long)L0 * L1;
             const long long up = (x2 + 1 == L2) ? -(long long)(L2 - 1) * st2 : st2;
             const long long dn = (x2 == 0) ? (long long)(L2 - 1) * st2 : -st2;
-            u2 = *reinterpret_cast<const Pack<real> *>(cur + off + up);
-            d2 = *reinterpret_cast<const Pack<real> *>(cur + off + dn);
+            u2p = *reinterpret_cast<const Pack<real> *>(cur + off + up);
+            d2p = *reinterpret_cast<const Pack<real> *>(cur + off + dn);
         }
         const real left = cur[(x0 == 0) ? off + L0 - 1 : off - 1];
         const real right = cur[(x0 + VEC == L0) ? off + VEC - L0 : off + VEC];
 
         // ---- per-site: draw, update ------------------------------------------------------
         Pack<real> res;
+        Seed32 s32 = seed_split(s);
+        u64 cg = site_const(g0);
+        bool maybe = false;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             const u64 g = g0 + e;
-            u64 t1, t2;
-            bool overridden = false;
-            if (REBASE) {
+            unsigned u1, u2;
+            if (REBASE) {  // replay step: generic 64-bit path with the host-resolved entries
+                u64 t1, t2;
+                bool overridden = false;
                 for (int j = 0; j < A.n_rebase; ++j)
                     if (A.rebase[j].chain == chain && A.rebase[j].gid_start == g) s = A.rebase[j].seed;
-            }
-            lcg_draw(s, g, t1, t2);
-            if (REBASE) {
+                lcg_draw(s, g, t1, t2);
                 for (int j = 0; j < A.n_rebase; ++j)
                     if (A.rebase[j].chain == chain && A.rebase[j].ov_gid == g) {
                         t1 = A.rebase[j].ov_t1;
                         t2 = A.rebase[j].ov_t2;
                         overridden = true;
                     }
+                if (!overridden && lcg_event(s & LCG_MASK, t1, t2))
+                    atomicMin((unsigned long long *)A.event_key, event_key(A.step_index, chain, g));
+                s = lcg_next_seed(t2) & LCG_MASK;
+                u1 = (unsigned)(t1 >> 16);
+                u2 = (unsigned)(t2 >> 16);
+            } else {
+                site_draw(s32, cg, u1, u2);
+                cg += LCG_A;
+                maybe |= site_maybe_event(u1, u2);
             }
-            if (!overridden && lcg_event(s & LCG_MASK, t1, t2))
-                atomicMin((unsigned long long *)A.event_key, event_key(A.step_index, chain, g));
-            s = lcg_next_seed(t2) & LCG_MASK;
 
             real dw;
             if (MATH == 1) {
-                const float r = noise_fast(t1, t2);
-                if (sizeof(real) == 4) dw = (real)__fmul_rn(nscale_f, r);
-                else dw = (real)__dmul_rn(A.nscale, (double)r);
+                if (sizeof(real) == 4) dw = (real)site_noise_fast(u1, u2, k2_f);
+                else dw = (real)__dmul_rn(A.nscale, (double)site_noise_fast(u1, u2, 1.3862943611198906f));
             } else {
-                dw = (real)__dmul_rn(A.nscale, noise_accurate(t1, t2));
+                dw = (real)__dmul_rn(A.nscale, noise_accurate((u64)u1 << 16, (u64)u2 << 16));
             }
             const real phi = c.v[e];
             const real nbp = (e < VEC - 1) ? c.v[(e + 1) % VEC] : right;
             const real nbm = (e > 0) ? c.v[(e + VEC - 1) % VEC] : left;
             real sum = O::add(nbp, nbm);
             if (NDIM >= 3) {
-                sum = O::add(sum, u1.v[e]);
-                sum = O::add(sum, d1.v[e]);
+                sum = O::add(sum, u1p.v[e]);
+                sum = O::add(sum, d1p.v[e]);
             }
             if (NDIM >= 4) {
-                sum = O::add(sum, u2.v[e]);
-                sum = O::add(sum, d2.v[e]);
+                sum = O::add(sum, u2p.v[e]);
+                sum = O::add(sum, d2p.v[e]);
             }
             sum = O::add(sum, pp.v[e]);
             sum = O::add(sum, pm.v[e]);
             const real lap = O::fma(-(real)(2 * NDIM), phi, sum);
-            real F;
-            if (A.pot == 4) F = O::mul(phi, O::fma(lam, O::mul(phi, phi), m2));
-            else F = O::mul((real)2, phi);
             real v = O::fma(c_lap, lap, phi);
-            v = O::fma(-c_dt, F, v);
+            if (A.pot == 4) v = O::fma(-c_dt, O::mul(phi, O::fma(lam, O::mul(phi, phi), m2)), v);
+            else v = O::fma(-c_2dt, phi, v);  // (-c_dt)(2 phi) == (-2 c_dt) phi exactly
             v = O::add(v, dw);
-            if (v > (real)1000) { v = (real)1000; ++nclamp; }
-            else if (v < -(real)1000) { v = -(real)1000; ++nclamp; }
-            else if (!(v == v)) { v = (real)1000; ++nclamp; }
-            res.v[e] = v;
+            const real vc = (v < (real)1000) ? ((v > -(real)1000) ? v : -(real)1000) : (real)1000;  // NaN -> +1000
+            nclamp += (vc != v) ? 1u : 0u;
+            res.v[e] = vc;
             acc1 = O::add(acc1, phi);
             acc2 = O::fma(phi, phi, acc2);
         }
+        if (!REBASE && __builtin_expect(maybe, 0))
+            strip_events_cold(A.event_key, A.step_index, chain, s, g0, VEC);
         *reinterpret_cast<Pack<real> *>(dst + off) = res;
     }
 

@@ -52,6 +52,12 @@ __device__ __noinline__ void strip_events_cold(u64 *event_key_ptr, int step, u64
     }
 }
 
+// by value: taking the address of a register array would force it into local memory
+__device__ __noinline__ unsigned count_clamped_cold(float a, float b, float c, float d) {
+    return (fabsf(a) >= 1000.0f ? 1u : 0u) + (fabsf(b) >= 1000.0f ? 1u : 0u) + (fabsf(c) >= 1000.0f ? 1u : 0u) +
+           (fabsf(d) >= 1000.0f ? 1u : 0u);
+}
+
 struct SiteCoef {
     float c_lap;   // (float)(m dtau / a2f)
     float c_dt;    // (float)dtau
@@ -129,15 +135,15 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
     float *edge = smem;
     float *rs_all = smem + 2 * NR * 2 * T;
     uint4 *chain = reinterpret_cast<uint4 *>(rs_all + 2 * (NR + 1) * T);
-    SiteCoef C;
-    C.c_lap = (float)A.c_lap;
+    SiteCoef C;  // float constants are cast on the host: plain constant-bank operands, no F2F here
+    C.c_lap = A.c_lap_f;
     C.pot = A.pot;
-    C.c_dt = (float)A.c_dt;
-    C.c_2dt = 2.0f * C.c_dt;
-    C.m2 = (float)A.m2;
-    C.lam = (float)A.lam;
+    C.c_dt = A.c_dt_f;
+    C.c_2dt = A.c_2dt_f;
+    C.m2 = A.m2_f;
+    C.lam = A.lam_f;
     C.nscale_d = A.nscale;
-    C.k2 = (float)(2.0 * 0.6931471805599453 * A.nscale * A.nscale);
+    C.k2 = A.k2_f;
 
     // ---- load the band, set up the per-strip chain state -----------------------------------
     float phi[NR][W];
@@ -156,9 +162,11 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
     }
     const unsigned Pl = (unsigned)A.P, Ph = (unsigned)(A.P >> 32);
     // c = gid*A + B of the first site of row 0's strip; rows advance it by L0*A
-    unsigned c0l, c0h;
-    site_const((u64)r0 * L0 + W * t, c0l, c0h);
+    const u64 c0 = site_const((u64)r0 * L0 + W * t);
     const u64 rowA = (u64)L0 * LCG_A;
+    // where this thread publishes its boundary-row words (parity 0 / 1) and reads its neighbours'
+    unsigned long long *const pub0 = A.halo_ll + ((size_t)0 * nb + b) * 2 * L0 + W * t;
+    unsigned long long *const pub1 = A.halo_ll + ((size_t)1 * nb + b) * 2 * L0 + W * t;
 
     // edges of the initial field
 #pragma unroll
@@ -192,12 +200,7 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
         auto do_row = [&](int k, const float *cur, const float *up, const float *dn, float *out) {
             const float left = edge[((eb * NR + k) * 2 + 1) * T + tl];
             const float right = edge[((eb * NR + k) * 2 + 0) * T + tr];
-            unsigned cl, ch;
-            {
-                const u64 c = (((u64)c0h << 32) | c0l) + (u64)k * rowA;
-                cl = (unsigned)c;
-                ch = (unsigned)(c >> 32);
-            }
+            u64 c = c0 + (u64)k * rowA;
             const uint4 st = chain[k * T + t];
             Seed32 s{st.x, st.y};
             const Seed32 s_before = s;
@@ -206,8 +209,8 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
 #pragma unroll
             for (int e = 0; e < W; ++e) {
                 unsigned u1, u2;
-                site_draw(s, cl, ch, u1, u2);
-                site_const_next(cl, ch);
+                site_draw(s, c, u1, u2);
+                c += LCG_A;
                 maybe |= site_maybe_event(u1, u2);
                 const float p = cur[e];
                 const float xp = (e < W - 1) ? cur[(e + 1) % W] : right;
@@ -219,10 +222,8 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
                 amax = fmaxf(amax, fabsf(out[e]));
             }
             // clamp hits (tau_kernel.cl:122-132) are counted on a cold path
-            if (__builtin_expect(amax >= 1000.0f, 0)) {
-#pragma unroll
-                for (int e = 0; e < W; ++e) myclamp += (fabsf(out[e]) >= 1000.0f) ? 1u : 0u;
-            }
+            if (__builtin_expect(amax >= 1000.0f, 0))
+                myclamp += count_clamped_cold(out[0], out[1], W > 2 ? out[W - 2] : 0.f, W > 2 ? out[W - 1] : 0.f);
             rs[k * T + t] = a;
             if (__builtin_expect(maybe, 0))
                 strip_events_cold(A.event_key, A.step_index0 + n, seed_join(s_before), (u64)(r0 + k) * L0 + W * t, W);
@@ -277,7 +278,7 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
         }
         if (n + 1 < A.nsteps) {  // {value, tag} words: no fence, no flag
             const unsigned tag = A.step0 + (unsigned)n + 1u;
-            unsigned long long *ho = A.halo_ll + ((size_t)((n + 1) & 1) * nb + b) * 2 * L0 + W * t;
+            unsigned long long *ho = eb ? pub0 : pub1;  // parity (n+1)&1
 #pragma unroll
             for (int e = 0; e < W; e += 2) {
                 *reinterpret_cast<ulonglong2 *>(ho + e) = make_ulonglong2(ll_pack(first[e], tag), ll_pack(first[e + 1], tag));

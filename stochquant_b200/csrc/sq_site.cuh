@@ -21,35 +21,26 @@ struct Seed32 {
 __device__ __forceinline__ Seed32 seed_split(u64 s) { return Seed32{(unsigned)s, (unsigned)(s >> 32)}; }
 __device__ __forceinline__ u64 seed_join(Seed32 s) { return (((u64)s.hi << 32) | s.lo) & LCG_MASK; }
 
-// x*A + c  (mod 2^64 in the low word, bits 32..47 valid in the high word)
-__device__ __forceinline__ void mad48(unsigned xl, unsigned xh, unsigned cl, unsigned ch, unsigned &rl, unsigned &rh) {
-    const u64 p = (u64)xl * A_LO + (((u64)ch << 32) | cl);  // IMAD.WIDE.U32 with 64-bit addend
+// x*A + c  (mod 2^64 in the low word, bits 32..47 valid in the high word); c stays a native
+// 64-bit value so the IMAD.WIDE addend needs no register-pair packing
+__device__ __forceinline__ void mad48(unsigned xl, unsigned xh, u64 c, unsigned &rl, unsigned &rh) {
+    const u64 p = (u64)xl * A_LO + c;                  // IMAD.WIDE.U32 with 64-bit addend
     rl = (unsigned)p;
-    rh = (unsigned)(p >> 32) + xl * A_HI + xh * A_LO;        // 2 x IMAD
+    rh = (unsigned)(p >> 32) + xl * A_HI + xh * A_LO;  // 2 x IMAD
 }
 
 // One draw at the site whose constant is c = gid*A + B.  Returns u1 = t1>>16, u2 = t2>>16 (32 bits
 // each) and advances the seed to t2 - 2^31 (event-free path, :281).
-__device__ __forceinline__ void site_draw(Seed32 &s, unsigned cl, unsigned ch, unsigned &u1, unsigned &u2) {
+__device__ __forceinline__ void site_draw(Seed32 &s, u64 c, unsigned &u1, unsigned &u2) {
     unsigned t1l, t1h, t2l, t2h;
-    mad48(s.lo, s.hi, cl, ch, t1l, t1h);      // t1 = (s+g)A + B = sA + c
+    mad48(s.lo, s.hi, c, t1l, t1h);           // t1 = (s+g)A + B = sA + c
     u1 = __funnelshift_r(t1l, t1h, 16);
-    mad48(t1l, t1h, cl, ch, t2l, t2h);        // t2 = (t1+g)A + B = t1 A + c
+    mad48(t1l, t1h, c, t2l, t2h);             // t2 = (t1+g)A + B = t1 A + c
     u2 = __funnelshift_r(t2l, t2h, 16);
     s.lo = t2l + 0x80000000u;                 // t2 - 2^31
     s.hi = t2h - (t2l < 0x80000000u ? 1u : 0u);
 }
-// c for the next gid: c += A
-__device__ __forceinline__ void site_const_next(unsigned &cl, unsigned &ch) {
-    const u64 c = ((((u64)ch << 32) | cl)) + LCG_A;
-    cl = (unsigned)c;
-    ch = (unsigned)(c >> 32);
-}
-__device__ __forceinline__ void site_const(u64 gid, unsigned &cl, unsigned &ch) {
-    const u64 c = gid * LCG_A + LCG_B;
-    cl = (unsigned)c;
-    ch = (unsigned)(c >> 32);
-}
+__device__ __forceinline__ u64 site_const(u64 gid) { return gid * LCG_A + LCG_B; }
 
 // Cheap necessary condition for an RNG event at this draw, given what the hot path has anyway:
 //   inf-retry  <=> u1 == 0
