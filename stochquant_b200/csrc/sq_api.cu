@@ -99,8 +99,10 @@ static int timing_mark(sq_ctx *c) {  // record the next pooled event on the stre
     CK(cudaEventRecord(c->ev_pool[c->ev_used++], c->stream));
     return SQ_OK;
 }
-static int timing_collect(sq_ctx *c) {  // after a stream sync: sum (start,stop) pairs
-    for (size_t i = 0; i + 1 < c->ev_used; i += 2) {
+// after a stream sync: sum the first `valid` (start,stop) pairs -- launches that were aborted
+// because an earlier one flagged an RNG event are not update-kernel time
+static int timing_collect(sq_ctx *c, size_t valid = (size_t)-1) {
+    for (size_t i = 0; i + 1 < c->ev_used && i / 2 < valid; i += 2) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]));
         c->timing_ms += ms;
@@ -604,10 +606,15 @@ static int sync_lattice(sq_ctx *c) {
     int64_t runs0 = c->pend_runs0;
     while (total > 0) {
         CK(cudaStreamSynchronize(c->stream));
-        if (c->timing) { int rt = timing_collect(c); if (rt) return rt; }
         u64 key;
         CK(cudaMemcpy(&key, c->l_event, sizeof(u64), cudaMemcpyDeviceToHost));
         const int n = c->pend_nsteps;
+        if (c->timing) {
+            size_t valid = (size_t)-1;  // streaming: launches up to and including the event step ran in full
+            if (key != NO_EVENT) valid = c->pend_kind == 1 ? 0 : (size_t)(key >> KEY_STEP_SHIFT) + 1;
+            int rt = timing_collect(c, valid);
+            if (rt) return rt;
+        }
         if (c->pend_kind == 1) {
             unsigned err = 0;
             CK(cudaMemcpy(&err, c->r_error, sizeof err, cudaMemcpyDeviceToHost));

@@ -109,10 +109,25 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
         const u64 g0 = gslice + off;
         // ---- seed before the draw at g0 ---------------------------------------------
         u64 s;
+        bool slow = false;  // REBASE: does a replay entry touch this strip?
         if (REBASE) {
             u64 bg, bs;
             rebase_lookup(A, chain, S, g0, bg, bs);
-            s = lcg_seed_at(bs, bg, g0 - bg, A.jump);
+            if (bg == 0) {  // still on the step's original chain: the precomputed jumps apply
+                const u64 ss = lcg_apply(A.slice_jump[tl], S, 0) & LCG_MASK;
+                s = lcg_apply(A.strip_jump[q % (unsigned)A.strips_per_cta_iter], ss, gslice) & LCG_MASK;
+                const unsigned rounds = q / (unsigned)A.strips_per_cta_iter;
+                for (unsigned r = 0; r < rounds; ++r)
+                    s = lcg_apply(A.stride_jump, s, gslice + (u64)(q % (unsigned)A.strips_per_cta_iter) * VEC +
+                                                        (u64)r * A.strips_per_cta_iter * VEC) & LCG_MASK;
+            } else {
+                s = lcg_seed_at(bs, bg, g0 - bg, A.jump);
+            }
+            for (int j = 0; j < A.n_rebase; ++j) {
+                const RebaseEntry e = A.rebase[j];
+                if (e.chain == chain && ((e.gid_start >= g0 && e.gid_start < g0 + VEC) || (e.ov_gid >= g0 && e.ov_gid < g0 + VEC)))
+                    slow = true;
+            }
         } else if (first) {
             // two precomputed jumps: to the slice start, then to this thread's first strip
             const u64 ss = lcg_apply(A.slice_jump[tl], S, 0) & LCG_MASK;
@@ -158,7 +173,7 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
         for (int e = 0; e < VEC; ++e) {
             const u64 g = g0 + e;
             unsigned u1, u2;
-            if (REBASE) {  // replay step: generic 64-bit path with the host-resolved entries
+            if (REBASE && slow) {  // a replay entry touches this strip: generic 64-bit path
                 u64 t1, t2;
                 bool overridden = false;
                 for (int j = 0; j < A.n_rebase; ++j)
@@ -213,7 +228,7 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
             acc1 = O::add(acc1, phi);
             acc2 = O::fma(phi, phi, acc2);
         }
-        if (!REBASE && __builtin_expect(maybe, 0))
+        if (!(REBASE && slow) && __builtin_expect(maybe, 0))
             strip_events_cold(A.event_key, A.step_index, chain, s, g0, VEC);
         *reinterpret_cast<Pack<real> *>(dst + off) = res;
     }
