@@ -6,8 +6,8 @@ NVCC  ?= nvcc
 ARCH  := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
 CSRC  := stochquant_b200/csrc
-OBJS  := $(CSRC)/sq_api.o $(CSRC)/sq_compat1d.o $(CSRC)/sq_lattice.o $(CSRC)/sq_resident.o
-HDRS  := include/sq.h $(CSRC)/sq_kernels.h $(CSRC)/sq_lcg.cuh $(CSRC)/sq_noise.cuh $(CSRC)/sq_site.cuh
+OBJS  := $(CSRC)/sq_api.o $(CSRC)/sq_compat1d.o $(CSRC)/sq_lattice.o $(CSRC)/sq_resident.o $(CSRC)/sq_slab.o $(CSRC)/sq_session.o
+HDRS  := include/sq.h $(CSRC)/sq_kernels.h $(CSRC)/sq_lcg.cuh $(CSRC)/sq_noise.cuh $(CSRC)/sq_site.cuh $(CSRC)/sq_ctx.h $(CSRC)/sq_session.h
 
 all: stochquant_b200/libsq.so tauhost.o oracle
 
@@ -15,7 +15,7 @@ $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; false)
 
 stochquant_b200/libsq.so: $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static -lrt
 
 # the drop-in executable keeps the reference's name (README.md:8 of the reference)
 tauhost.o: host/tauhost.c host/tauhost_io.c host/tauhost_io.h include/sq.h stochquant_b200/libsq.so

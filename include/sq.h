@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SQ_API_VERSION 1
+#define SQ_API_VERSION 2
 
 /* error codes */
 #define SQ_OK 0
@@ -33,7 +33,8 @@ extern "C" {
 #define SQ_ERR_NOMEM (-3)
 #define SQ_ERR_UNSUPPORTED (-4) /* e.g. potential ids 1,2: no kernel in reference */
 #define SQ_ERR_NODEVICE (-5)
-#define SQ_ERR_TIMEOUT (-6)     /* bounded device-side wait expired (halo flags)  */
+#define SQ_ERR_TIMEOUT (-6)     /* bounded wait expired (halo flags, session barrier) */
+#define SQ_ERR_INTERNAL (-7)    /* an invariant of the library was violated          */
 
 /* which kernel family */
 enum {
@@ -179,13 +180,52 @@ int sq_debug_draws(sq_ctx *ctx, int chain, uint64_t gid0, uint64_t n, uint64_t *
  * Lets a caller position the shared chain (tau_kernel.cl:269-284) for a slab or a resume. */
 uint64_t sq_lcg_jump(uint64_t seed, uint64_t gid0, uint64_t ndraws);
 
-/* ---- multi-GPU slabs (one process per GPU; handles are exchanged by the caller,
- * e.g. with torch.distributed) -------------------------------------------------- */
-#define SQ_IPC_HANDLE_BYTES 256
-int sq_slab_export(sq_ctx *ctx, void *handle /* SQ_IPC_HANDLE_BYTES */);
-/* lower/upper: handles of the ranks owning the slabs below/above in time
- * (periodic).  Pass this context's own handle for a 1-rank ring. */
-int sq_slab_attach(sq_ctx *ctx, const void *lower, const void *upper);
+/* ---- multi-GPU slab decomposition (north_star (4)) --------------------
+ * The reference is single-device (tauhost.c:249-252: one context, one in-order queue); this is
+ * new work behind the same four entry points.  One lattice is cut along its time axis into slabs,
+ * one context per GPU (sq_params.slab_t0/slab_nt), one process or host thread per context, all on
+ * ONE box.  The ranks meet in a session (POSIX shared memory: barrier + small all-gathers; no GPU
+ * needed); sq_slab_join then maps the ring neighbours' halo arenas (CUDA IPC, or plain peer
+ * pointers inside one process) and from then on
+ *   - the boundary slices travel GPU-to-GPU over NVLink inside the update kernel itself
+ *     (boundary slices first, posted peer stores, arrival flags; no host in the loop);
+ *   - every rank draws from the ONE shared-seed chain of tau_kernel.cl:269-284 at its global
+ *     gids; the chain's rare data-dependent events (inf-retry :282, `seed+=` :278-279) are
+ *     found ahead of the update by an integer-only scan of each slab and agreed on through the
+ *     session, so all ranks apply the same corrections and the stream stays bit-exact;
+ *   - the running means of Phi(t)Phi(t_mid) use the mid slice's owner's per-step sums.
+ * With a joined context sq_step / sq_step_async / sq_sync / sq_measure are COLLECTIVE: every
+ * rank of the ring must make the same calls with the same dtau / nsteps / runs0. */
+typedef struct sq_session sq_session;
+/* name: unique per ring (no '/'); the segment is unlinked once every rank has attached */
+int sq_session_open(sq_session **out, const char *name, int rank, int nranks);
+int sq_session_barrier(sq_session *s);
+/* n <= 8 words per rank; out: [nranks][n] */
+int sq_session_allgather_u64(sq_session *s, const uint64_t *in, int n, uint64_t *out);
+/* n <= 3072 doubles per rank; out: [nranks][n] */
+int sq_session_allgather_f64(sq_session *s, const double *in, int n, double *out);
+void sq_session_abort(sq_session *s); /* wake every waiter with SQ_ERR_TIMEOUT */
+int sq_session_rank(const sq_session *s);
+int sq_session_size(const sq_session *s);
+void sq_session_close(sq_session *s);
+
+/* Collective.  The contexts' slabs must tile [0, Lt) in rank order; seeds must agree.  The
+ * session must outlive the context (close it after sq_free). */
+int sq_slab_join(sq_ctx *ctx, sq_session *s);
+/* statistics of a joined context: finder kernel launches and agreement rounds so far */
+int sq_slab_stats(sq_ctx *ctx, uint64_t *finder_scans, uint64_t *agree_rounds);
+
+/* One resolved event of the shared-seed chain within a tau-step: draws at gid >= gid_start
+ * continue from `seed`; the draw at ov_gid used (ov_t1, ov_t2). */
+typedef struct sq_rng_entry {
+    uint64_t gid_start, seed, ov_gid, ov_t1, ov_t2;
+} sq_rng_entry;
+/* Host-side utility (no GPU needed): replay the draw at `gid` literally (tau_kernel.cl:269-284,
+ * including the do/while retry) given the step-start seed and the step's earlier entries
+ * (ascending gid).  Every rank of a ring calls this with the same arguments and gets the same
+ * entry.  *ndraws = LCG double-draws consumed (1 = no retry), *plus = the `seed+=` branch taken. */
+int sq_rng_resolve(uint64_t step_seed, const sq_rng_entry *entries, int n, uint64_t gid,
+                   sq_rng_entry *out, int *ndraws, int *plus);
 
 #ifdef __cplusplus
 }

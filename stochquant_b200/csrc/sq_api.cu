@@ -10,87 +10,18 @@
 #include <new>
 #include <vector>
 
-#include "../../include/sq.h"
-#include "sq_kernels.h"
+#include "sq_ctx.h"
 
 using namespace sq;
 
-static thread_local char g_cuda_err[512] = "";
+static thread_local char g_cuda_err_tls[512] = "";
+namespace sq {
+char *cuda_err_buf() { return g_cuda_err_tls; }
+}
+#define g_cuda_err (sq::cuda_err_buf())
 
-#define CK(call)                                                                               \
-    do {                                                                                       \
-        cudaError_t e__ = (call);                                                              \
-        if (e__ != cudaSuccess) {                                                              \
-            snprintf(g_cuda_err, sizeof g_cuda_err, "%s at %s:%d: %s", #call, __FILE__, __LINE__, \
-                     cudaGetErrorString(e__));                                                 \
-            return SQ_ERR_CUDA;                                                                \
-        }                                                                                      \
-    } while (0)
 
-static constexpr int MAX_SEQ_STEPS = 32768;  // step field of the event key has 16 bits
-static constexpr int MAX_REBASE = 64;
-static constexpr int RES_MAX_STEPS = 2048;  // tau-steps per resident launch (history buffer)
-static constexpr int RES_MAX_ROWS = 8;
-
-struct sq_ctx {
-    sq_params p{};
-    cudaStream_t stream = nullptr;
-    JumpEntry *d_jump = nullptr;
-    std::vector<JumpEntry> h_jump;
-    int64_t launches = 0;
-    int64_t runs = 0;
-    int last_stable = 1;
-    int64_t last_steps = 0;
-    uint64_t nevents = 0;
-    void *h_pin = nullptr;  // pinned scratch (4 KB)
-
-    // ---- compat 1-D ----
-    double *c_f = nullptr, *c_x = nullptr, *c_xx0 = nullptr, *c_newf = nullptr, *c_newx = nullptr,
-           *c_newxx0 = nullptr, *c_omega = nullptr, *c_lrgVl = nullptr, *c_red = nullptr;
-    u64 *c_seed = nullptr, *c_nevents = nullptr;
-    int *c_stable = nullptr, *c_lrgEl = nullptr, *c_steps = nullptr;
-
-    // ---- lattice ----
-    void *l_field[2] = {nullptr, nullptr};
-    void *l_ghost[2] = {nullptr, nullptr};  // local halo buffers (slab mode without P2P)
-    u64 *l_seeds[2] = {nullptr, nullptr};
-    u64 *l_event = nullptr;
-    RebaseEntry *l_rebase = nullptr;
-    JumpEntry *l_slice_jump = nullptr, *l_strip_jump = nullptr;
-    double *l_partials = nullptr, *l_slice_sum = nullptr, *l_slice_x = nullptr, *l_slice_xx0 = nullptr,
-           *l_sums = nullptr, *l_sums_mean = nullptr, *l_m2 = nullptr, *l_lam = nullptr, *l_redbuf = nullptr;
-    unsigned long long *l_nclamped = nullptr;
-    int cur = 0;
-    int nt = 0, ctas_per_slice = 1;
-    int64_t vslice = 0, V = 0, vlocal = 0;
-    size_t rsz = 4;
-    bool per_chain_coupling = false;
-    // resident 2-D path (sq_resident.cu)
-    bool res_ok = false;
-    int res_nb = 0, res_rows = 0;
-    unsigned long long *r_halo = nullptr;
-    unsigned *r_error = nullptr;
-    unsigned r_tag = 1;     // monotonic halo tag base (never reused, also across replays)
-    double *r_hist_rows = nullptr, *r_hist_p2 = nullptr, *r_step_sums = nullptr;
-    int res_limit = 0;      // >0: the next resident batch must stop after this many steps
-    int force_stream = 0;   // >0: this many steps must go through the streaming kernel
-    int pend_kind = 0;      // 0 streaming, 1 resident
-    // pending sequence
-    bool pending = false;
-    double pend_dtau = 0;
-    int pend_nsteps = 0;  // steps currently enqueued
-    int pend_total = 0;   // steps the caller asked for
-    int64_t pend_runs0 = 0;
-    std::vector<RebaseEntry> entries;  // replay entries valid for the first step of the sequence
-    // optional per-launch timing of the update kernel
-    bool timing = false;
-    std::vector<cudaEvent_t> ev_pool;
-    size_t ev_used = 0;
-    double timing_ms = 0;
-    int64_t timing_launches = 0;
-};
-
-static int timing_mark(sq_ctx *c) {  // record the next pooled event on the stream
+int sq_timing_mark(sq_ctx *c) {  // record the next pooled event on the stream
     if (c->ev_used == c->ev_pool.size()) {
         cudaEvent_t e;
         CK(cudaEventCreate(&e));
@@ -101,7 +32,7 @@ static int timing_mark(sq_ctx *c) {  // record the next pooled event on the stre
 }
 // after a stream sync: sum the first `valid` (start,stop) pairs -- launches that were aborted
 // because an earlier one flagged an RNG event are not update-kernel time
-static int timing_collect(sq_ctx *c, size_t valid = (size_t)-1) {
+int sq_timing_collect(sq_ctx *c, size_t valid) {
     for (size_t i = 0; i + 1 < c->ev_used && i / 2 < valid; i += 2) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, c->ev_pool[i], c->ev_pool[i + 1]));
@@ -113,7 +44,7 @@ static int timing_collect(sq_ctx *c, size_t valid = (size_t)-1) {
 }
 
 // ------------------------------------------------------------------- helpers --------------
-static int set_dev(sq_ctx *c) {
+int sq_set_dev(sq_ctx *c) {
     CK(cudaSetDevice(c->p.device));
     return SQ_OK;
 }
@@ -133,7 +64,8 @@ extern "C" const char *sq_strerror(int code) {
         case SQ_ERR_NOMEM: return "out of memory";
         case SQ_ERR_UNSUPPORTED: return "unsupported (no kernel for this potential / mode in the reference)";
         case SQ_ERR_NODEVICE: return "no usable CUDA device (libsq has no CPU fallback)";
-        case SQ_ERR_TIMEOUT: return "device-side wait timed out";
+        case SQ_ERR_TIMEOUT: return "bounded wait timed out (halo flag or session barrier)";
+        case SQ_ERR_INTERNAL: return "internal invariant violated";
     }
     return "unknown error";
 }
@@ -143,7 +75,7 @@ extern "C" int sq_device_count(void) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess) {
-        snprintf(g_cuda_err, sizeof g_cuda_err, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        snprintf(g_cuda_err, 512, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
         return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? 0 : -1;
     }
     return n;
@@ -164,6 +96,7 @@ extern "C" void sq_free(sq_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->p.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    sq_slab_destroy(c);
     void *ptrs[] = {c->d_jump, c->c_f, c->c_x, c->c_xx0, c->c_newf, c->c_newx, c->c_newxx0, c->c_omega,
                     c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps,
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
@@ -335,10 +268,10 @@ extern "C" int sq_init(sq_ctx **out, const sq_params *p, const double *f0, const
     c->p = *p;
     int rc = SQ_OK;
     do {
-        if ((rc = set_dev(c))) break;
+        if ((rc = sq_set_dev(c))) break;
         cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
         if (e != cudaSuccess) {
-            snprintf(g_cuda_err, sizeof g_cuda_err, "cudaStreamCreate: %s", cudaGetErrorString(e));
+            snprintf(g_cuda_err, 512, "cudaStreamCreate: %s", cudaGetErrorString(e));
             rc = SQ_ERR_CUDA;
             break;
         }
@@ -384,14 +317,14 @@ static int enqueue_compat(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     A.newf = c->c_newf; A.newx = c->c_newx; A.newxx0 = c->c_newxx0;
     A.omega = c->c_omega; A.seed = c->c_seed; A.stable = c->c_stable;
     A.lrgEl = c->c_lrgEl; A.lrgVl = c->c_lrgVl; A.steps_done = c->c_steps; A.nevents = c->c_nevents;
-    if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+    if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     CK(launch_compat1d(A, c->stream));
-    if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+    if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     c->launches++;
     return SQ_OK;
 }
 
-static LatticeArgs lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */) {
+LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */) {
     const sq_params &p = c->p;
     LatticeArgs A{};
     const int vec = (int)(16 / c->rsz);
@@ -440,7 +373,7 @@ static LatticeArgs lattice_args(sq_ctx *c, double dtau, int k /* step in sequenc
 
 static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     const sq_params &p = c->p;
-    LatticeArgs A = lattice_args(c, dtau, 0);
+    LatticeArgs A = sq_lattice_args(c, dtau, 0);
     const int Lt = (int)p.dims[p.ndim - 1];
     const int tmid = Lt / 2;
     for (int k = 0; k < nsteps; ++k) {
@@ -451,9 +384,9 @@ static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
         A.seed_in = c->l_seeds[b];
         A.seed_out = c->l_seeds[b ^ 1];
         A.n_rebase = (k == 0) ? (int)c->entries.size() : 0;
-        if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+        if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
         CK(launch_lattice_step(A, p.real, p.math, c->ctas_per_slice, c->stream));
-        if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+        if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
         c->launches++;
         if (A.partials) {
             FinalizeArgs F{};
@@ -480,7 +413,7 @@ static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
 
 static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     const sq_params &p = c->p;
-    const LatticeArgs L = lattice_args(c, dtau, 0);
+    const LatticeArgs L = sq_lattice_args(c, dtau, 0);
     ResidentArgs A{};
     A.L0 = (int)p.dims[0];
     A.L1 = (int)p.dims[1];
@@ -518,10 +451,10 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     A.error_flag = c->r_error;
     // per-chain couplings live in device arrays for the streaming kernel; the resident kernel is
     // single-chain and takes them by value: keep both in sync through sq_set_chain (host mirror)
-    if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+    if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     static const int strip_w = getenv("SQ_RESIDENT_STRIP") ? atoi(getenv("SQ_RESIDENT_STRIP")) : 0;  // tuning knob
     CK(launch_resident2d(A, p.math, c->res_nb, c->res_rows, strip_w, c->stream));
-    if (c->timing) { int rt = timing_mark(c); if (rt) return rt; }
+    if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     c->launches++;
     WelfordArgs W{};
     W.nt = c->nt;
@@ -566,7 +499,7 @@ static int enqueue_batch(sq_ctx *c, int remaining, int64_t runs0) {
 extern "C" int sq_step_async(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     if (!c || nsteps < 0 || !(dtau > 0)) return SQ_ERR_INVALID;
     if (c->pending) return SQ_ERR_INVALID;
-    int rc = set_dev(c);
+    int rc = sq_set_dev(c);
     if (rc) return rc;
     c->pend_dtau = dtau;
     c->pend_nsteps = nsteps;
@@ -574,6 +507,8 @@ extern "C" int sq_step_async(sq_ctx *c, double dtau, int nsteps, int64_t runs0) 
     c->pend_runs0 = runs0;
     if (c->p.kernel == SQ_KERNEL_COMPAT1D) {
         if (nsteps > 0 && (rc = enqueue_compat(c, dtau, nsteps, runs0))) return rc;
+    } else if (c->slab) {
+        if ((rc = sq_slab_enqueue(c, dtau, nsteps, runs0))) return rc;
     } else if (nsteps > 0) {
         if ((rc = enqueue_batch(c, nsteps, runs0))) return rc;
     }
@@ -582,7 +517,7 @@ extern "C" int sq_step_async(sq_ctx *c, double dtau, int nsteps, int64_t runs0) 
 }
 
 // seed (full u64) before the draw at gid g of the step whose start seed is S, under `entries`
-static u64 host_seed_before(const sq_ctx *c, const std::vector<RebaseEntry> &entries, int chain, u64 S, u64 g) {
+u64 sq_host_seed_before(const sq_ctx *c, const std::vector<RebaseEntry> &entries, int chain, u64 S, u64 g) {
     u64 bg = 0, bs = S;
     for (const RebaseEntry &e : entries)
         if (e.chain == chain && e.gid_start <= g && e.gid_start >= bg) { bg = e.gid_start; bs = e.seed; }
@@ -612,7 +547,7 @@ static int sync_lattice(sq_ctx *c) {
         if (c->timing) {
             size_t valid = (size_t)-1;  // streaming: launches up to and including the event step ran in full
             if (key != NO_EVENT) valid = c->pend_kind == 1 ? 0 : (size_t)(key >> KEY_STEP_SHIFT) + 1;
-            int rt = timing_collect(c, valid);
+            int rt = sq_timing_collect(c, valid);
             if (rt) return rt;
         }
         if (c->pend_kind == 1) {
@@ -642,7 +577,7 @@ static int sync_lattice(sq_ctx *c) {
                 const u64 g = key & ((1ULL << KEY_CHAIN_SHIFT) - 1);
                 u64 S;
                 CK(cudaMemcpy(&S, c->l_seeds[c->cur] + chain, sizeof(u64), cudaMemcpyDeviceToHost));
-                const u64 sfull = host_seed_before(c, c->entries, chain, S, g);
+                const u64 sfull = sq_host_seed_before(c, c->entries, chain, S, g);
                 const HostDraw h = host_draw_literal(sfull, g);
                 RebaseEntry e{};
                 e.gid_start = g + 1;
@@ -682,11 +617,11 @@ extern "C" int sq_sync(sq_ctx *c, int *stable) {
         if (stable) *stable = c->last_stable;
         return SQ_OK;
     }
-    int rc = set_dev(c);
+    int rc = sq_set_dev(c);
     if (rc) return rc;
     if (c->p.kernel == SQ_KERNEL_COMPAT1D) {
         CK(cudaStreamSynchronize(c->stream));
-        if (c->timing) { int rt = timing_collect(c); if (rt) return rt; }
+        if (c->timing) { int rt = sq_timing_collect(c, (size_t)-1); if (rt) return rt; }
         if (c->pend_nsteps > 0) {
             int st = 1, steps = 0;
             CK(cudaMemcpy(&st, c->c_stable, sizeof(int), cudaMemcpyDeviceToHost));
@@ -701,7 +636,7 @@ extern "C" int sq_sync(sq_ctx *c, int *stable) {
             }
         }
     } else {
-        rc = sync_lattice(c);
+        rc = c->slab ? sq_slab_finish(c) : sync_lattice(c);
         if (rc) { c->pending = false; return rc; }
     }
     c->pending = false;
@@ -719,7 +654,7 @@ extern "C" int sq_step(sq_ctx *c, double dtau, int nsteps, int64_t runs0, int *s
 extern "C" int sq_measure(sq_ctx *c, sq_obs *o) {
     if (!c || !o || o->struct_size != sizeof(sq_obs)) return SQ_ERR_INVALID;
     if (c->pending) return SQ_ERR_INVALID;
-    int rc = set_dev(c);
+    int rc = sq_set_dev(c);
     if (rc) return rc;
     const sq_params &p = c->p;
     o->runs = c->runs;
@@ -785,12 +720,13 @@ extern "C" int sq_measure(sq_ctx *c, sq_obs *o) {
         const double xm = (tm >= 0 && tm < nt) ? sx[(size_t)tm] : 0.;
         for (int t = 0; t < nt; ++t) o->corr[t] = sxx[t] - sx[t] * xm;
     }
+    if (c->slab) sq_slab_measure(c, o);  // joined ring: running means and the seed live on the host
     return SQ_OK;
 }
 
 extern "C" int sq_measure_chains(sq_ctx *c, double *mean_phi, double *mean_phi2, uint64_t *seeds) {
     if (!c || c->p.kernel != SQ_KERNEL_LATTICE || c->pending) return SQ_ERR_INVALID;
-    int rc = set_dev(c);
+    int rc = sq_set_dev(c);
     if (rc) return rc;
     const int nc = c->p.nchains;
     double *buf = nullptr;
@@ -819,7 +755,7 @@ extern "C" int sq_measure_chains(sq_ctx *c, double *mean_phi, double *mean_phi2,
 static int field_xfer(sq_ctx *c, int chain, void *host, int real, bool upload) {
     if (!c || !host || c->p.kernel != SQ_KERNEL_LATTICE || c->pending) return SQ_ERR_INVALID;
     if (chain < 0 || chain >= c->p.nchains || (real != SQ_REAL_F32 && real != SQ_REAL_F64)) return SQ_ERR_INVALID;
-    int rc = set_dev(c);
+    int rc = sq_set_dev(c);
     if (rc) return rc;
     char *dev = (char *)c->l_field[c->cur] + (size_t)chain * c->vlocal * c->rsz;
     const size_t hsz = real == SQ_REAL_F32 ? 4 : 8;
@@ -855,7 +791,7 @@ extern "C" int sq_download_field(sq_ctx *c, int chain, void *host, int real) {
 extern "C" int sq_set_chain(sq_ctx *c, int chain, uint64_t seed, double m2, double lambda) {
     if (!c || c->p.kernel != SQ_KERNEL_LATTICE || c->pending) return SQ_ERR_INVALID;
     if (chain < 0 || chain >= c->p.nchains) return SQ_ERR_INVALID;
-    int rc = set_dev(c);
+    int rc = sq_set_dev(c);
     if (rc) return rc;
     CK(cudaMemcpy(c->l_seeds[c->cur] + chain, &seed, sizeof(u64), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->l_m2 + chain, &m2, sizeof(double), cudaMemcpyHostToDevice));
@@ -871,7 +807,7 @@ extern "C" int sq_set_chain(sq_ctx *c, int chain, uint64_t seed, double m2, doub
 extern "C" int sq_frame_host(sq_ctx *c, const void *host_in, void *host_out, int real, double dtau, int nsteps,
                              int64_t runs0, sq_obs *obs, int *stable) {
     if (!c || c->pending) return SQ_ERR_INVALID;
-    int rc = set_dev(c);
+    int rc = sq_set_dev(c);
     if (rc) return rc;
     if (c->p.kernel == SQ_KERNEL_COMPAT1D) {
         if (real != SQ_REAL_F64) return SQ_ERR_INVALID;
@@ -900,7 +836,7 @@ extern "C" int sq_frame_host(sq_ctx *c, const void *host_in, void *host_out, int
 // ------------------------------------------------------------------- parity hook ----------
 extern "C" int sq_debug_draws(sq_ctx *c, int chain, uint64_t gid0, uint64_t n, uint64_t *t1, uint64_t *t2) {
     if (!c || c->pending || !t1 || !t2) return SQ_ERR_INVALID;
-    int rc = set_dev(c);
+    int rc = sq_set_dev(c);
     if (rc) return rc;
     u64 seed = 0;
     if (c->p.kernel == SQ_KERNEL_COMPAT1D) {
@@ -949,12 +885,8 @@ extern "C" uint64_t sq_lcg_jump(uint64_t seed, uint64_t gid0, uint64_t ndraws) {
     return lcg_seed_at(seed, gid0, ndraws, tab.data());
 }
 
-// ------------------------------------------------------------------- slabs (stub stage) ---
-extern "C" int sq_slab_export(sq_ctx *c, void *handle) {
-    if (!c || !handle) return SQ_ERR_INVALID;
-    return SQ_ERR_UNSUPPORTED;
-}
-extern "C" int sq_slab_attach(sq_ctx *c, const void *lower, const void *upper) {
-    if (!c || !lower || !upper) return SQ_ERR_INVALID;
-    return SQ_ERR_UNSUPPORTED;
+extern "C" int sq_slab_stats(sq_ctx *c, uint64_t *finder_scans, uint64_t *agree_rounds) {
+    if (!c) return SQ_ERR_INVALID;
+    sq_slab_stats_impl(c, finder_scans, agree_rounds);
+    return SQ_OK;
 }

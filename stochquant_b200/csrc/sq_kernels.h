@@ -79,6 +79,16 @@ struct LatticeArgs {
     u64 *event_key;      // atomicMin target; != NO_EVENT also aborts later launches
     double *partials;    // [nchains][nt][ctas_per_slice][2] (sum phi, sum phi^2), or null
     unsigned long long *nclamped;
+    // ---- multi-GPU slab ring (sq_slab.cu); slab_on == 0: everything below is unused ----------
+    // direction 0 = the slice below local slice 0, 1 = the slice above local slice nt-1.
+    int slab_on;
+    unsigned wait_tag;             // ghost_lo/ghost_hi are valid once *wait_flag[d] has reached this tag
+    const unsigned *wait_flag[2];  // local arrival flags of this step's ghost buffers
+    unsigned push_tag;             // tag of the field this step produces; 0: do not push (last step)
+    void *push_ghost[2];           // [0]: lower neighbour's "above" ghost, [1]: upper neighbour's "below" ghost
+    unsigned *push_flag[2];        // the neighbours' arrival flags for those buffers
+    unsigned *push_count;          // local [2]: CTAs of the boundary slice that have finished
+    unsigned *slab_error;          // bounded waits: raised instead of hanging the GPU
 };
 cudaError_t launch_lattice_step(const LatticeArgs &A, int real, int math, int ctas_per_slice,
                                 cudaStream_t stream);
@@ -94,7 +104,7 @@ struct FinalizeArgs {
     double *slice_xx0;   // [nchains][nt]   running mean of Phi(t) Phi(t_mid)
     double *sums;        // [nchains][2]    last step's global sums (phi, phi^2)
     double *sums_mean;   // [nchains][2]    running means of <phi>, <phi^2>
-    double *history;     // slab mode: [nt] slice sums of this step appended, else null
+    double *history;     // slab mode: this step's [nt] slice sums + (sum phi, sum phi^2), else null
     const u64 *event_key;
 };
 cudaError_t launch_finalize(const FinalizeArgs &A, cudaStream_t stream);

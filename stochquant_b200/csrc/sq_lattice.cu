@@ -70,6 +70,26 @@ __device__ __noinline__ void strip_events_cold(u64 *event_key_ptr, int step, int
     }
 }
 
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// slab ring: wait until the neighbour's boundary slice of this step's input field has landed in the
+// local ghost buffer (tags are monotonic, so ">=" in wrap-around arithmetic).  Bounded.
+__device__ __noinline__ void slab_wait(const unsigned *flag, unsigned want, unsigned *err) {
+    for (unsigned spins = 0; (int)(ld_acquire_sys_u32(flag) - want) < 0; ++spins) {
+        __nanosleep(64);
+        if (spins > (1u << 24)) {  // ~ seconds: the neighbour is gone
+            atomicExch(err, 1u);
+            return;
+        }
+    }
+}
+
 }  // namespace
 
 template <typename real, int MATH, int NDIM, bool REBASE>
@@ -78,7 +98,19 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
     constexpr int VEC = 16 / sizeof(real);
     if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;  // an earlier launch must be replayed
 
-    const int chain = blockIdx.z, tl = blockIdx.y;
+    const int chain = blockIdx.z;
+    // slab ring: the two boundary slices are scheduled first so that their output reaches the
+    // neighbours while the interior slices are still being computed
+    int tl = blockIdx.y;
+    if (A.slab_on && A.nt > 1) tl = (blockIdx.y == 0) ? 0 : ((blockIdx.y == 1) ? A.nt - 1 : (int)blockIdx.y - 1);
+    const bool edge_lo = A.slab_on && tl == 0, edge_hi = A.slab_on && tl == A.nt - 1;
+    if (edge_lo | edge_hi) {
+        if (threadIdx.x == 0) {
+            if (edge_lo) slab_wait(A.wait_flag[0], A.wait_tag, A.slab_error);
+            if (edge_hi) slab_wait(A.wait_flag[1], A.wait_tag, A.slab_error);
+        }
+        __syncthreads();
+    }
     const long long vs = A.vslice;
     const real *in = (const real *)A.in + (long long)chain * A.chain_stride;
     real *out = (real *)A.out + (long long)chain * A.chain_stride;
@@ -86,6 +118,8 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
     const real *tm = (tl > 0) ? cur - vs : (A.wrap_time ? in + (long long)(A.nt - 1) * vs : (const real *)A.ghost_lo);
     const real *tp = (tl < A.nt - 1) ? cur + vs : (A.wrap_time ? in : (const real *)A.ghost_hi);
     real *dst = out + (long long)tl * vs;
+    real *push_lo = (edge_lo && A.push_tag) ? (real *)A.push_ghost[0] : nullptr;
+    real *push_hi = (edge_hi && A.push_tag) ? (real *)A.push_ghost[1] : nullptr;
 
     const u64 gslice = (u64)(A.slab_t0 + tl) * (u64)vs;
     const u64 S = A.seed_in[chain];
@@ -231,6 +265,25 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
         if (!(REBASE && slow) && __builtin_expect(maybe, 0))
             strip_events_cold(A.event_key, A.step_index, chain, s, g0, VEC);
         *reinterpret_cast<Pack<real> *>(dst + off) = res;
+        // boundary slices also go straight into the neighbours' ghost buffers (posted NVLink writes)
+        if (push_lo) *reinterpret_cast<Pack<real> *>(push_lo + off) = res;
+        if (push_hi) *reinterpret_cast<Pack<real> *>(push_hi + off) = res;
+    }
+    if (push_lo || push_hi) {  // last CTA of the slice: everything is out, raise the neighbour's flag
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (push_lo && atomicAdd(A.push_count + 0, 1u) == gridDim.x - 1) {
+                A.push_count[0] = 0;
+                __threadfence_system();
+                st_release_sys_u32(A.push_flag[0], A.push_tag);
+            }
+            if (push_hi && atomicAdd(A.push_count + 1, 1u) == gridDim.x - 1) {
+                A.push_count[1] = 0;
+                __threadfence_system();
+                st_release_sys_u32(A.push_flag[1], A.push_tag);
+            }
+        }
     }
 
     // ---- the omega work-item's draw (gid = V) and the step's final seed -----------------
@@ -310,6 +363,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs A) {
         for (int t = 0; t < A.nt; ++t) { a += s1[t]; b += s2[t]; }
         A.sums[chain * 2] = a;
         A.sums[chain * 2 + 1] = b;
+        if (A.history && chain == 0) {
+            A.history[A.nt] = a;
+            A.history[A.nt + 1] = b;
+        }
         const double n = (double)(A.runs + 1);
         const double vol = (double)A.vslice * (double)A.nt;
         A.sums_mean[chain * 2] += (a / vol - A.sums_mean[chain * 2]) / n;

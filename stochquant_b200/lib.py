@@ -17,7 +17,6 @@ SQ_MATH_ACCURATE, SQ_MATH_FAST = 0, 1
 SQ_POT_HARMONIC, SQ_POT_DOUBLEWELL, SQ_POT_PHI4 = 0, 3, 4
 SQ_FLAG_NO_OBSERVABLES = 1
 SQ_FLAG_FORCE_STREAMING = 2
-SQ_IPC_HANDLE_BYTES = 256
 
 
 class SqError(RuntimeError):
@@ -44,6 +43,11 @@ class SqObs(C.Structure):
                 ("slice_x", C.POINTER(C.c_double)), ("slice_xx0", C.POINTER(C.c_double)),
                 ("corr", C.POINTER(C.c_double)), ("nclamped", C.c_int64),
                 ("nevents", C.c_uint64), ("steps_done", C.c_int64)]
+
+
+class SqRngEntry(C.Structure):
+    _fields_ = [("gid_start", C.c_uint64), ("seed", C.c_uint64), ("ov_gid", C.c_uint64),
+                ("ov_t1", C.c_uint64), ("ov_t2", C.c_uint64)]
 
 
 def library_path() -> str:
@@ -121,16 +125,95 @@ def load() -> C.CDLL:
     L.sq_kernel_time.argtypes = [vp, pd, C.POINTER(i64)]
     L.sq_lcg_jump.restype = u64
     L.sq_lcg_jump.argtypes = [u64, u64, u64]
-    L.sq_slab_export.restype = i32
-    L.sq_slab_export.argtypes = [vp, vp]
-    L.sq_slab_attach.restype = i32
-    L.sq_slab_attach.argtypes = [vp, vp, vp]
+    L.sq_session_open.restype = i32
+    L.sq_session_open.argtypes = [C.POINTER(vp), C.c_char_p, i32, i32]
+    L.sq_session_barrier.restype = i32
+    L.sq_session_barrier.argtypes = [vp]
+    L.sq_session_allgather_u64.restype = i32
+    L.sq_session_allgather_u64.argtypes = [vp, C.POINTER(u64), i32, C.POINTER(u64)]
+    L.sq_session_allgather_f64.restype = i32
+    L.sq_session_allgather_f64.argtypes = [vp, pd, i32, pd]
+    L.sq_session_abort.restype = None
+    L.sq_session_abort.argtypes = [vp]
+    L.sq_session_rank.restype = i32
+    L.sq_session_rank.argtypes = [vp]
+    L.sq_session_size.restype = i32
+    L.sq_session_size.argtypes = [vp]
+    L.sq_session_close.restype = None
+    L.sq_session_close.argtypes = [vp]
+    L.sq_slab_join.restype = i32
+    L.sq_slab_join.argtypes = [vp, vp]
+    L.sq_slab_stats.restype = i32
+    L.sq_slab_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.sq_rng_resolve.restype = i32
+    L.sq_rng_resolve.argtypes = [u64, C.POINTER(SqRngEntry), i32, u64, C.POINTER(SqRngEntry),
+                                 C.POINTER(i32), C.POINTER(i32)]
     _lib = L
     return L
 
 
 def _dp(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _check(L, rc, what):
+    if rc != 0:
+        raise SqError(rc, what, (L.sq_strerror(rc) or b"").decode() + "; " + (L.sq_last_cuda_error() or b"").decode())
+
+
+class Session:
+    """Rendezvous of the ranks of one slab ring on one box (POSIX shared memory; no GPU needed)."""
+
+    def __init__(self, name: str, rank: int, nranks: int):
+        self.L = load()
+        self._h = C.c_void_p()
+        _check(self.L, self.L.sq_session_open(C.byref(self._h), name.encode(), rank, nranks), "sq_session_open")
+        self.rank, self.nranks = rank, nranks
+
+    def barrier(self):
+        _check(self.L, self.L.sq_session_barrier(self._h), "sq_session_barrier")
+
+    def allgather_u64(self, words) -> np.ndarray:
+        a = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1)
+        out = np.zeros((self.nranks, a.size), dtype=np.uint64)
+        p64 = C.POINTER(C.c_uint64)
+        _check(self.L, self.L.sq_session_allgather_u64(self._h, a.ctypes.data_as(p64), a.size, out.ctypes.data_as(p64)),
+               "sq_session_allgather_u64")
+        return out
+
+    def allgather_f64(self, vals) -> np.ndarray:
+        a = np.ascontiguousarray(vals, dtype=np.float64).reshape(-1)
+        out = np.zeros((self.nranks, a.size))
+        _check(self.L, self.L.sq_session_allgather_f64(self._h, _dp(a), a.size, _dp(out)), "sq_session_allgather_f64")
+        return out
+
+    def abort(self):
+        if self._h.value:
+            self.L.sq_session_abort(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.L.sq_session_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def rng_resolve(step_seed: int, entries: list, gid: int):
+    """sq_rng_resolve: literal replay of the draw at gid -> (entry dict, ndraws, plus)."""
+    L = load()
+    arr = (SqRngEntry * max(1, len(entries)))()
+    for k, e in enumerate(entries):
+        for f, _ in SqRngEntry._fields_:
+            setattr(arr[k], f, int(e[f]))
+    out, nd, pl = SqRngEntry(), C.c_int(), C.c_int()
+    _check(L, L.sq_rng_resolve(int(step_seed) & (2**64 - 1), arr, len(entries), int(gid), C.byref(out), C.byref(nd),
+                               C.byref(pl)), "sq_rng_resolve")
+    return {f: int(getattr(out, f)) for f, _ in SqRngEntry._fields_}, nd.value, pl.value
 
 
 class Context:
@@ -194,6 +277,16 @@ class Context:
 
     def __exit__(self, *a):
         self.close()
+
+    def join(self, session: "Session"):
+        """Collective: make this context one slab of the ring behind `session` (sq_slab_join)."""
+        self._check(self.L.sq_slab_join(self._h, session._h), "sq_slab_join")
+        self._session = session  # must outlive the context
+
+    def slab_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self.L.sq_slab_stats(self._h, C.byref(a), C.byref(b)), "sq_slab_stats")
+        return {"finder_scans": a.value, "agree_rounds": b.value}
 
     @property
     def stream(self) -> int:

@@ -1,0 +1,134 @@
+"""GPU parity of the multi-GPU slab decomposition (north_star (4)): a ring of contexts,
+each owning a slab of time slices, must reproduce the whole-lattice oracle (oracle/sq_oracle.c:
+sqo_lattice_step) -- seeds bit-exact, fields within the single-GPU tolerances, running means of the
+slice observables across slabs.
+
+Rings of 1-3 ranks run as host threads on ONE GPU (plain peer pointers inside the process: the halo
+protocol, the finder and the event agreement are the same code as across GPUs); the 2-process ring
+over CUDA IPC needs two GPUs and runs where they exist (gpurun --gpus 2)."""
+import os
+import subprocess
+import sys
+import threading
+import uuid
+
+import numpy as np
+import pytest
+
+from helpers import maxabs, seed_with_retry_at
+from slab_common import run_rank, split_slabs
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ATOL = {("f64", "accurate"): 5e-7, ("f32", "accurate"): 2e-5, ("f32", "fast"): 6e-5}
+DTAU = 0.01
+
+
+def ring_threads(sq, nranks, dims, phi0, frames, **kw):
+    name = "t" + uuid.uuid4().hex[:12]
+    res, err = [None] * nranks, []
+
+    def work(r):
+        try:
+            res[r] = run_rank(sq, name, r, nranks, dims, phi0, frames, DTAU, **kw)
+        except Exception as e:  # noqa: BLE001
+            err.append((r, e))
+    th = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(300)
+    assert not err, err
+    assert all(r is not None for r in res)
+    return res
+
+
+def check_against_oracle(res, o, dims, tol_field, tol_obs):
+    vs = int(np.prod(dims[:-1]))
+    tm = dims[-1] // 2
+    for r in res:
+        t0, nt = r["t0"], r["nt"]
+        assert r["seed"] == o.seed, "step seed must be bit-exact on every rank"
+        assert r["runs"] == o.L.runs
+        err = maxabs(r["field"], o.field[t0 * vs:(t0 + nt) * vs])
+        assert err < tol_field, (t0, err)
+        assert maxabs(r["slice_x"], o.slice_x[t0:t0 + nt]) < tol_obs
+        assert maxabs(r["slice_xx0"], o.slice_xx0[t0:t0 + nt]) < tol_obs
+        assert maxabs(r["corr"], (o.slice_xx0 - o.slice_x * o.slice_x[tm])[t0:t0 + nt]) < tol_obs
+        assert r["nclamped"] == 0
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("dims,real,math,pot", [((16, 8, 4, 12), "f32", "accurate", 4), ((64, 24), "f64", "accurate", 0),
+                                               ((32, 8, 9), "f32", "fast", 4)])
+def test_ring_vs_oracle(gpu_sq, oracle, nranks, dims, real, math, pot):
+    rng = np.random.default_rng(5)
+    phi0 = rng.normal(size=int(np.prod(dims))) * 0.5
+    o = oracle.LatticeOracle(dims, real=oracle.F32 if real == "f32" else oracle.F64, potential=pot, m2=0.25, lam=0.5,
+                             phi0=phi0)
+    frames = [1, 2, 14]
+    res = ring_threads(gpu_sq, nranks, dims, phi0, frames, real=real, math=math, pot=pot, m2=0.25, lam=0.5)
+    o.step(DTAU, sum(frames))
+    check_against_oracle(res, o, dims, ATOL[(real, math)], 50 * ATOL[(real, math)])
+    # one finder scan per step and rank at least
+    assert all(r["stats"]["finder_scans"] >= sum(frames) for r in res)
+
+
+@pytest.mark.parametrize("where", ["slab0", "slab1", "slab2_last", "omega", "plus"])
+def test_ring_events_agreed(gpu_sq, oracle, where):
+    """An RNG event (inf-retry / `seed+=`) in one slab changes the seeds of every later draw on
+    every rank: found by the finder, agreed through the session, applied everywhere."""
+    dims = (16, 4, 12)
+    V = 16 * 4 * 12
+    vs = 64
+    seed = {"plus": 39512}.get(where)
+    if seed is None:
+        g = {"slab0": 3 * vs + 5, "slab1": 5 * vs + 17, "slab2_last": V - 1, "omega": V}[where]
+        seed = seed_with_retry_at(oracle, g)
+    rng = np.random.default_rng(6)
+    phi0 = rng.normal(size=V) * 0.5
+    o = oracle.LatticeOracle(dims, real=oracle.F64, potential=0, seed=seed, phi0=phi0)
+    res = ring_threads(gpu_sq, 3, dims, phi0, [6], real="f64", math="accurate", seed=seed)
+    o.step(DTAU, 6)
+    assert o.L.nevents >= 1
+    check_against_oracle(res, o, dims, ATOL[("f64", "accurate")], 1e-5)
+    assert all(r["nevents"] >= 1 for r in res)
+
+
+def test_ring_equals_single_context(gpu_sq):
+    """Same lattice, whole vs 4 slabs: the fields must be IDENTICAL bit for bit (same kernel, same
+    operation order, same stream) and so must the slice sums."""
+    dims = (32, 8, 4, 16)
+    rng = np.random.default_rng(7)
+    phi0 = (rng.normal(size=int(np.prod(dims))) * 0.5).astype(np.float32)
+    whole = gpu_sq.Context(dims, real="f32", math="fast", potential=4, m2=0.25, lam=0.5)
+    whole.upload(phi0)
+    whole.step(DTAU, 11)
+    ref = whole.download()
+    res = ring_threads(gpu_sq, 4, dims, phi0, [11], real="f32", math="fast", pot=4, m2=0.25, lam=0.5)
+    got = np.concatenate([r["field"] for r in res])
+    assert np.array_equal(got, ref)
+    m = whole.measure()
+    assert maxabs(np.concatenate([r["slice_x"] for r in res]), m["slice_x"]) < 1e-12
+    assert maxabs(np.concatenate([r["slice_xx0"] for r in res]), m["slice_xx0"]) < 1e-12
+
+
+def test_two_process_ring_over_ipc(gpu_sq, oracle, tmp_path):
+    """One process per GPU, halo arenas mapped through CUDA IPC, NVLink peer stores: needs 2 GPUs."""
+    if gpu_sq.load().sq_device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    dims = (32, 16, 8, 20)
+    name = "p" + uuid.uuid4().hex[:12]
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "slab_worker.py"), name, str(r), "2",
+                               ",".join(map(str, dims)), str(tmp_path / f"r{r}.npz")]) for r in range(2)]
+    for p in procs:
+        assert p.wait(300) == 0
+    rng = np.random.default_rng(9)
+    phi0 = rng.normal(size=int(np.prod(dims))) * 0.5
+    o = oracle.LatticeOracle(dims, real=oracle.F32, potential=4, m2=0.25, lam=0.5, phi0=phi0)
+    o.step(DTAU, 25)
+    res = []
+    for r, (t0, nt) in enumerate(split_slabs(dims[-1], 2)):
+        z = np.load(tmp_path / f"r{r}.npz")
+        res.append({k: (z[k] if z[k].ndim else z[k].item()) for k in z.files} | {"t0": t0, "nt": nt})
+    check_against_oracle(res, o, dims, ATOL[("f32", "accurate")], 50 * ATOL[("f32", "accurate")])
