@@ -41,6 +41,11 @@ WORKLOADS = {
                desc="configs[2]: 4-D 64^4 fp32, 100 tau-steps per step"),
     "slab": dict(dims=(256, 256, 256, 32), real="f32", pot=0, m2=0.0, lam=0.0, dtau=0.01, loops=10,
                  desc="configs[3] per-GPU slab: 256^3 x 32 fp32 (x8 GPUs = 256^4)"),
+    # one lattice, slab-decomposed along the time axis over the N ranks (strong scaling)
+    "c4": dict(dims=(256, 256, 256, 256), real="f32", pot=0, m2=0.0, lam=0.0, dtau=0.01, loops=10, ring=True,
+               desc="configs[3]: 4-D 256^4 fp32, time slabs over N GPUs, halos over NVLink inside the update kernel"),
+    "c4s": dict(dims=(256, 256, 256, 64), real="f32", pot=0, m2=0.0, lam=0.0, dtau=0.01, loops=10, ring=True,
+                desc="configs[3] at quarter size: 256^3 x 64 fp32, time slabs over N GPUs"),
 }
 BYTES_PER_UPDATE = {"f32": 8, "f64": 16}  # one read + one write of phi
 
@@ -193,8 +198,23 @@ def main():
     V = int(np.prod(dims))
     # N > 1: each rank advances its own independent lattice of the same shape (north_star (4):
     # independent chains spread across GPUs, no data-path communication) -> weak scaling
-    ctx = sq.Context(dims, real=wl["real"], math=args.math, potential=wl["pot"], m2=wl["m2"], lam=wl["lam"],
-                     device=local, seed=1242608872 + rank)
+    ring = bool(wl.get("ring"))
+    sess = None
+    if ring:
+        # north_star (4): ONE lattice in time slabs, one per rank; total work fixed -> strong scaling
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from slab_common import split_slabs
+        slab = split_slabs(dims[-1], world)[rank]
+        sess = sq.Session(f"bench{os.environ.get('MASTER_PORT', os.getpid())}", rank, world)
+        ctx = sq.Context(dims, real=wl["real"], math=args.math, potential=wl["pot"], m2=wl["m2"], lam=wl["lam"],
+                         device=local, seed=1242608872, slab=slab)
+        ctx.join(sess)
+        args.no_e2e = True          # a 17 GB pinned host frame per step is not this workload's use
+        args.no_cpu_baseline = True
+    else:
+        ctx = sq.Context(dims, real=wl["real"], math=args.math, potential=wl["pot"], m2=wl["m2"], lam=wl["lam"],
+                         device=local, seed=1242608872 + rank)
+    nshare = 1 if ring else world   # lattices advanced by the job
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -231,7 +251,7 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = world * V * loops * args.steps / (total_ms * 1e-3)
+    value = nshare * V * loops * args.steps / (total_ms * 1e-3)
 
     # ---- roofline: the update kernel alone, CUDA events around every launch -------------
     ctx.kernel_timing(True)
@@ -240,7 +260,8 @@ def main():
     ctx.kernel_timing(False)
     peak, peak_src = peaks()
     bpu = BYTES_PER_UPDATE[wl["real"]]
-    units_per_launch = V * loops / max(kn, 1)
+    Vloc = ctx.vlocal  # sites one launch of this rank's kernel updates
+    units_per_launch = Vloc * loops / max(kn, 1)
     ach = units_per_launch * bpu / (kms / max(kn, 1) * 1e-3) / 1e9
     traffic, tnote = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -248,7 +269,7 @@ def main():
         try:
             t = json.load(open(tp)).get(name)
             # ncu capture of one launch, scaled to the tau-steps one launch covers in this run
-            traffic = t["bytes_per_launch"] * (units_per_launch / V / t["tau_steps_per_launch"]) \
+            traffic = t["bytes_per_launch"] * (units_per_launch / Vloc / t["tau_steps_per_launch"]) \
                 if "lattice_step" in t["kernel"] else t["bytes_per_launch"]
             tnote = t["source"]
         except Exception:
@@ -257,7 +278,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": tnote,
                 "kernel": "resident2d_kernel" if resident else "lattice_step_kernel", "launches_timed": kn,
-                "tau_steps_per_launch": units_per_launch / V,
+                "tau_steps_per_launch": units_per_launch / Vloc,
                 "avg_launch_us": 1e3 * kms / max(kn, 1), "bytes_per_site_update": bpu, "peak_source": peak_src,
                 "note": ("on-chip resident kernel: the 4 MiB lattice is read/written once per launch, so `achieved` "
                          "(algorithmic bytes / time) measures instruction efficiency against the HBM roofline"
@@ -294,17 +315,20 @@ def main():
     if rank == 0:
         line = {"metric": "lattice site-updates/s", "value": value, "unit": "site-updates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": wl["real"],
-                "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if ring else "weak", "vs_baseline": None,
+                "dtype": wl["real"], "data": "synthetic",
                 "config": {"workload": name, "desc": wl["desc"], "dims": list(dims), "dtau": dtau,
                            "tau_steps_per_step": loops, "potential": wl["pot"], "math": args.math,
-                           "seed": 1242608872, "l2": "flushed between timed steps (256 MB write); lattice itself "
-                           "is smaller than L2", "parallelism": f"{world} independent lattice(s), one per GPU"},
+                           "seed": 1242608872, "l2": "flushed between timed steps (256 MB write)", "parallelism": (f"one lattice in {world} time slab(s), NVLink halo ring" if ring else
+                                           f"{world} independent lattice(s), one per GPU"),
+                           "slab": ctx.slab_stats() if ring else None},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     ctx.close()
+    if sess is not None:
+        sess.close()
 
 
 if __name__ == "__main__":

@@ -101,7 +101,7 @@ extern "C" void sq_free(sq_ctx *c) {
                     c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps,
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
-                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_slice_jump, c->l_strip_jump,
+                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump,
                     c->r_halo, c->r_error, c->r_hist_rows, c->r_hist_p2, c->r_step_sums};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -183,6 +183,28 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
     int64_t cps = (nstrips + 256 * 4 - 1) / (256 * 4);
     if (cps < 1) cps = 1;
     c->ctas_per_slice = (int)std::min<int64_t>(cps, 65535);
+    // row-marching kernel (sq_march.cu): fp32, d >= 3, dims[0]/4 threads per row a power of two
+    if (p.real == SQ_REAL_F32 && p.ndim >= 3 && !(p.flags & SQ_FLAG_GENERIC_KERNEL)) {
+        const int64_t L0 = p.dims[0], L1 = p.dims[1], tpr = L0 / 4;
+        if (L0 % 4 == 0 && tpr >= 1 && tpr <= 256 && (tpr & (tpr - 1)) == 0) {
+            const int64_t rg = 256 / tpr, nrows = c->vslice / L0;
+            int best = 0;
+            for (int R = 16; R >= 1; R >>= 1) {
+                if (L1 % R != 0 || nrows % (rg * R) != 0) continue;
+                if (!best) best = R;  // the largest that fits ...
+                const int64_t ctas = nrows / (rg * R) * c->nt * p.nchains;
+                if (ctas >= 148 * 12) { best = R; break; }  // ... unless a smaller one is needed to fill the GPU
+                best = R;
+            }
+            if (best && nrows / (rg * best) <= 65535) {
+                c->march_ok = true;
+                c->m_R = best;
+                c->m_tpr_log = 0;
+                while ((1 << c->m_tpr_log) < tpr) c->m_tpr_log++;
+                c->ctas_per_slice = (int)(nrows / (rg * best));
+            }
+        }
+    }
 
     const size_t fbytes = (size_t)c->vlocal * c->rsz * (size_t)p.nchains;
     for (int b = 0; b < 2; ++b) {
@@ -216,6 +238,16 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
         CK(cudaMalloc((void **)&c->l_strip_jump, sizeof(JumpEntry) * qj.size()));
         CK(cudaMemcpy(c->l_slice_jump, sj.data(), sizeof(JumpEntry) * sj.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->l_strip_jump, qj.data(), sizeof(JumpEntry) * qj.size(), cudaMemcpyHostToDevice));
+        if (c->march_ok) {
+            const u64 L0 = (u64)p.dims[0], tpr = L0 / 4, rows_per_cta = (256 / tpr) * (u64)c->m_R;
+            std::vector<JumpEntry> cj((size_t)c->ctas_per_slice), tj(256);
+            for (size_t b = 0; b < cj.size(); ++b) cj[b] = jump_entry((u64)b * rows_per_cta * L0);
+            for (u64 t = 0; t < 256; ++t) tj[t] = jump_entry((t / tpr) * (u64)c->m_R * L0 + (t % tpr) * 4);
+            CK(cudaMalloc((void **)&c->l_cta_jump, sizeof(JumpEntry) * cj.size()));
+            CK(cudaMalloc((void **)&c->l_thr_jump, sizeof(JumpEntry) * tj.size()));
+            CK(cudaMemcpy(c->l_cta_jump, cj.data(), sizeof(JumpEntry) * cj.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(c->l_thr_jump, tj.data(), sizeof(JumpEntry) * tj.size(), cudaMemcpyHostToDevice));
+        }
     }
     std::vector<u64> seeds((size_t)p.nchains);
     std::vector<double> m2((size_t)p.nchains, p.m2), lam((size_t)p.nchains, p.lambda);
@@ -324,6 +356,13 @@ static int enqueue_compat(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     return SQ_OK;
 }
 
+void sq_fill_rebase_inline(LatticeArgs &A, const RebaseEntry *e, int n) {
+    for (int j = 0; j < RB_INLINE; ++j) {
+        A.rb_gid[j] = (j < n && n <= RB_INLINE) ? e[j].gid_start : ~0ULL;
+        A.rb_chain[j] = (j < n && n <= RB_INLINE) ? e[j].chain : -1;
+    }
+}
+
 LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */) {
     const sq_params &p = c->p;
     LatticeArgs A{};
@@ -336,6 +375,14 @@ LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */
     A.step_index = k;
     A.n_rebase = 0;
     A.strips_per_cta_iter = 256 * c->ctas_per_slice;
+    {   // L2 blocking (sq_lattice.cu): one chunk = ~6 MB of each time level
+        const double bytes_per_cta = (double)c->vslice * (double)c->rsz / (double)c->ctas_per_slice;
+        static const double chunk_mb = getenv("SQ_CHUNK_MB") ? atof(getenv("SQ_CHUNK_MB")) : 6.0;  // tuning knob
+        long long cpc = (long long)(chunk_mb * 1048576.0 / bytes_per_cta);
+        if (cpc < 1) cpc = 1;
+        if (cpc > c->ctas_per_slice) cpc = c->ctas_per_slice;
+        A.ctas_per_chunk = (int)cpc;
+    }
     for (int i = 0; i < 4; ++i) A.dim[i] = i < p.ndim ? p.dims[i] : 1;
     A.vslice = c->vslice;
     A.V = c->V;
@@ -364,11 +411,24 @@ LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */
     A.stride_jump = jump_entry((u64)A.strips_per_cta_iter * (u64)vec);
     A.vol_jump = jump_entry((u64)c->V);
     A.jump = c->d_jump;
+    A.m_on = c->march_ok ? 1 : 0;
+    A.m_R = c->m_R;
+    A.m_tpr_log = c->m_tpr_log;
+    A.cta_jump = c->l_cta_jump;
+    A.thr_jump = c->l_thr_jump;
+    A.row_jump = jump_entry((u64)p.dims[0]);
     A.rebase = c->l_rebase;
+    sq_fill_rebase_inline(A, nullptr, 0);
     A.event_key = c->l_event;
     A.partials = (p.flags & SQ_FLAG_NO_OBSERVABLES) ? nullptr : c->l_partials;
     A.nclamped = c->l_nclamped;
     return A;
+}
+
+int sq_launch_update(sq_ctx *c, const LatticeArgs &A) {
+    if (A.m_on) CK(launch_lattice_march(A, c->p.math, c->ctas_per_slice, c->stream));
+    else CK(launch_lattice_step(A, c->p.real, c->p.math, c->ctas_per_slice, c->stream));
+    return SQ_OK;
 }
 
 static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
@@ -384,8 +444,9 @@ static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
         A.seed_in = c->l_seeds[b];
         A.seed_out = c->l_seeds[b ^ 1];
         A.n_rebase = (k == 0) ? (int)c->entries.size() : 0;
+        sq_fill_rebase_inline(A, c->entries.data(), A.n_rebase);
         if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
-        CK(launch_lattice_step(A, p.real, p.math, c->ctas_per_slice, c->stream));
+        { int rl = sq_launch_update(c, A); if (rl) return rl; }
         if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
         c->launches++;
         if (A.partials) {

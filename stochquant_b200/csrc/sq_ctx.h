@@ -64,6 +64,10 @@ struct sq_ctx {
     int64_t vslice = 0, V = 0, vlocal = 0;
     size_t rsz = 4;
     bool per_chain_coupling = false;
+    // row-marching kernel (sq_march.cu): geometry + jump tables, when the shape qualifies
+    bool march_ok = false;
+    int m_R = 0, m_tpr_log = 0;
+    JumpEntry *l_cta_jump = nullptr, *l_thr_jump = nullptr;
     // resident 2-D path (sq_resident.cu)
     bool res_ok = false;
     int res_nb = 0, res_rows = 0;
@@ -96,6 +100,8 @@ int sq_set_dev(sq_ctx *c);
 int sq_timing_mark(sq_ctx *c);
 int sq_timing_collect(sq_ctx *c, size_t valid);
 sq::LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k);
+int sq_launch_update(sq_ctx *c, const sq::LatticeArgs &A);  // generic or marching kernel
+void sq_fill_rebase_inline(sq::LatticeArgs &A, const sq::RebaseEntry *e, int n);
 // seed (full u64) before the draw at gid g of the step whose start seed is S, under `entries`
 sq::u64 sq_host_seed_before(const sq_ctx *c, const std::vector<sq::RebaseEntry> &entries, int chain, sq::u64 S, sq::u64 g);
 // sq_slab.cu

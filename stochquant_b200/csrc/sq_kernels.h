@@ -47,6 +47,7 @@ struct RebaseEntry {
     int pad;
 };
 
+constexpr int RB_INLINE = 4;
 struct LatticeArgs {
     int ndim;            // 2..4
     int pot;             // 0 | 4
@@ -56,6 +57,8 @@ struct LatticeArgs {
     int step_index;      // position in the current launch sequence (event key)
     int n_rebase;        // entries valid for this step
     int strips_per_cta_iter;  // blockDim.x * gridDim.x
+    int ctas_per_chunk;  // L2 blocking: CTAs sweep a chunk of this many CTAs' sites through ALL time slices
+                         // before moving to the next chunk (chunk x 4 slices must fit in L2)
     long long dim[4];    // extents, dim[ndim-1] = global Lt
     long long vslice;    // sites per time slice
     long long V;         // global volume (= draws per step - 1)
@@ -76,9 +79,20 @@ struct LatticeArgs {
     JumpEntry vol_jump;      // jump over V draws from gid 0 (to the omega draw)
     const JumpEntry *jump;
     const RebaseEntry *rebase;
+    // the entries' gid_start (ascending, padded with ~0) and chains by value: strips test them
+    // from the constant bank; more than RB_INLINE entries take the generic path
+    u64 rb_gid[4];
+    int rb_chain[4];
     u64 *event_key;      // atomicMin target; != NO_EVENT also aborts later launches
     double *partials;    // [nchains][nt][ctas_per_slice][2] (sum phi, sum phi^2), or null
     unsigned long long *nclamped;
+    // ---- row-marching kernel (sq_march.cu), fp32 d = 3,4 with dims[0]/4 a power of two <= 256 ----
+    int m_on;                    // 1: launch lattice_march_kernel (gridDim.x = its own CTAs per slice)
+    int m_R;                     // consecutive rows (x1) per thread; divides dims[1]
+    int m_tpr_log;               // log2(threads per row) = log2(dims[0] / 4)
+    const JumpEntry *cta_jump;   // [ctas per slice] jump over bx * rows_per_cta * L0 draws
+    const JumpEntry *thr_jump;   // [256] jump over (ty * R * L0 + tx * 4) draws
+    JumpEntry row_jump;          // jump over L0 draws (one row down at fixed x0)
     // ---- multi-GPU slab ring (sq_slab.cu); slab_on == 0: everything below is unused ----------
     // direction 0 = the slice below local slice 0, 1 = the slice above local slice nt-1.
     int slab_on;
@@ -92,6 +106,7 @@ struct LatticeArgs {
 };
 cudaError_t launch_lattice_step(const LatticeArgs &A, int real, int math, int ctas_per_slice,
                                 cudaStream_t stream);
+cudaError_t launch_lattice_march(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream);
 
 struct FinalizeArgs {
     int nt, nchains, ctas_per_slice;

@@ -16,93 +16,20 @@
 //     later strips of the grid-stride loop: one fixed-stride jump);
 //   * per-slice sum(phi), sum(phi^2): registers -> warp shuffle -> one fp64 partial per
 //     CTA, reduced in fixed order by finalize_kernel (bit-reproducible, no float atomics).
-#include "sq_kernels.h"
-#include "sq_site.cuh"
+#include "sq_lattice_common.cuh"
 
 namespace sq {
 
-namespace {
-
-template <typename real>
-struct alignas(16) Pack {
-    real v[16 / sizeof(real)];
-};
-
-template <typename real> struct Ops;
-template <> struct Ops<float> {
-    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-};
-template <> struct Ops<double> {
-    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
-};
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// base (gid, seed) applicable to draws starting at gid g under the step's rebase list
-__device__ __forceinline__ void rebase_lookup(const LatticeArgs &A, int chain, u64 S, u64 g,
-                                              u64 &bg, u64 &bs) {
-    bg = 0;
-    bs = S;
-    for (int j = 0; j < A.n_rebase; ++j) {
-        const RebaseEntry e = A.rebase[j];
-        if (e.chain == chain && e.gid_start <= g && e.gid_start >= bg) {
-            bg = e.gid_start;
-            bs = e.seed;
-        }
-    }
-}
-
-// cold paths, arguments by value (taking the address of a register array would spill it)
-__device__ __noinline__ void strip_events_cold(u64 *event_key_ptr, int step, int chain, u64 sm, u64 g0, int w) {
-    for (int e = 0; e < w; ++e) {
-        u64 t1, t2;
-        lcg_draw(sm, g0 + e, t1, t2);
-        if (lcg_event(sm, t1, t2)) atomicMin((unsigned long long *)event_key_ptr, event_key(step, chain, g0 + e));
-        sm = lcg_next_seed(t2) & LCG_MASK;
-    }
-}
-
-__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// slab ring: wait until the neighbour's boundary slice of this step's input field has landed in the
-// local ghost buffer (tags are monotonic, so ">=" in wrap-around arithmetic).  Bounded.
-__device__ __noinline__ void slab_wait(const unsigned *flag, unsigned want, unsigned *err) {
-    for (unsigned spins = 0; (int)(ld_acquire_sys_u32(flag) - want) < 0; ++spins) {
-        __nanosleep(64);
-        if (spins > (1u << 24)) {  // ~ seconds: the neighbour is gone
-            atomicExch(err, 1u);
-            return;
-        }
-    }
-}
-
-}  // namespace
-
 template <typename real, int MATH, int NDIM, bool REBASE>
-__global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) {
+__global__ void __launch_bounds__(256, (REBASE || NDIM == 4 || sizeof(real) == 8) ? 3 : 5) lattice_step_kernel(const LatticeArgs A) {
     using O = Ops<real>;
     constexpr int VEC = 16 / sizeof(real);
     if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;  // an earlier launch must be replayed
 
     const int chain = blockIdx.z;
-    // slab ring: the two boundary slices are scheduled first so that their output reaches the
-    // neighbours while the interior slices are still being computed
-    int tl = blockIdx.y;
-    if (A.slab_on && A.nt > 1) tl = (blockIdx.y == 0) ? 0 : ((blockIdx.y == 1) ? A.nt - 1 : (int)blockIdx.y - 1);
+    int tl;
+    unsigned bx;
+    cta_slice_position(A, tl, bx);
     const bool edge_lo = A.slab_on && tl == 0, edge_hi = A.slab_on && tl == A.nt - 1;
     if (edge_lo | edge_hi) {
         if (threadIdx.x == 0) {
@@ -136,32 +63,48 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
     real acc1 = 0, acc2 = 0;
     unsigned nclamp = 0;
     u64 s_prev = 0, g_prev = 0;
+    unsigned cnt_prev = 0;
     bool first = true;
 
-    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < nstrips; q += (unsigned)A.strips_per_cta_iter) {
+    for (unsigned q = bx * blockDim.x + threadIdx.x; q < nstrips; q += (unsigned)A.strips_per_cta_iter) {
         const unsigned off = q * VEC;
         const u64 g0 = gslice + off;
         // ---- seed before the draw at g0 ---------------------------------------------
         u64 s;
         bool slow = false;  // REBASE: does a replay entry touch this strip?
         if (REBASE) {
-            u64 bg, bs;
-            rebase_lookup(A, chain, S, g0, bg, bs);
-            if (bg == 0) {  // still on the step's original chain: the precomputed jumps apply
-                const u64 ss = lcg_apply(A.slice_jump[tl], S, 0) & LCG_MASK;
-                s = lcg_apply(A.strip_jump[q % (unsigned)A.strips_per_cta_iter], ss, gslice) & LCG_MASK;
-                const unsigned rounds = q / (unsigned)A.strips_per_cta_iter;
-                for (unsigned r = 0; r < rounds; ++r)
-                    s = lcg_apply(A.stride_jump, s, gslice + (u64)(q % (unsigned)A.strips_per_cta_iter) * VEC +
-                                                        (u64)r * A.strips_per_cta_iter * VEC) & LCG_MASK;
+            // how many entries lie at or before this strip (they are sorted): the last of them is the
+            // strip's base.  While that number does not change between a thread's strips the
+            // ordinary stride jump applies; only a change of base pays a table jump.
+            unsigned cnt = 0;
+            if (A.n_rebase <= RB_INLINE) {
+#pragma unroll
+                for (int j = 0; j < RB_INLINE; ++j) {
+                    const bool mine = (j < A.n_rebase) & (A.rb_chain[j] == chain);
+                    cnt += (mine & (A.rb_gid[j] <= g0)) ? 1u : 0u;
+                    slow |= mine & (A.rb_gid[j] - g0 <= (u64)VEC);  // gid_start or ov_gid (= gid_start-1) inside
+                }
             } else {
-                s = lcg_seed_at(bs, bg, g0 - bg, A.jump);
+                for (int j = 0; j < A.n_rebase; ++j) {
+                    const RebaseEntry e = A.rebase[j];
+                    const bool mine = e.chain == chain;
+                    cnt += (mine & (e.gid_start <= g0)) ? 1u : 0u;
+                    slow |= mine & (e.gid_start - g0 <= (u64)VEC);
+                }
             }
-            for (int j = 0; j < A.n_rebase; ++j) {
-                const RebaseEntry e = A.rebase[j];
-                if (e.chain == chain && ((e.gid_start >= g0 && e.gid_start < g0 + VEC) || (e.ov_gid >= g0 && e.ov_gid < g0 + VEC)))
-                    slow = true;
+            if (first || cnt != cnt_prev) {
+                if (cnt == 0 && first) {
+                    const u64 ss = lcg_apply(A.slice_jump[tl], S, 0) & LCG_MASK;
+                    s = lcg_apply(A.strip_jump[q], ss, gslice) & LCG_MASK;
+                } else {
+                    u64 bg, bs;
+                    rebase_lookup(A, chain, S, g0, bg, bs);
+                    s = lcg_seed_at(bs, bg, g0 - bg, A.jump);
+                }
+            } else {
+                s = lcg_apply(A.stride_jump, s_prev, g_prev) & LCG_MASK;
             }
+            cnt_prev = cnt;
         } else if (first) {
             // two precomputed jumps: to the slice start, then to this thread's first strip
             const u64 ss = lcg_apply(A.slice_jump[tl], S, 0) & LCG_MASK;
@@ -287,7 +230,7 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
     }
 
     // ---- the omega work-item's draw (gid = V) and the step's final seed -----------------
-    if (blockIdx.x == 0 && tl == 0 && threadIdx.x == 0) {
+    if (bx == 0 && tl == 0 && threadIdx.x == 0) {
         const u64 Vg = (u64)A.V;
         u64 s, t1, t2;
         bool overridden = false;
@@ -323,7 +266,7 @@ __global__ void __launch_bounds__(256) lattice_step_kernel(const LatticeArgs A) 
         if (threadIdx.x == 0) {
             double s1 = 0, s2 = 0;
             for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { s1 += red[0][k]; s2 += red[1][k]; }
-            double *p = A.partials + (((long long)chain * A.nt + tl) * gridDim.x + blockIdx.x) * 2;
+            double *p = A.partials + (((long long)chain * A.nt + tl) * gridDim.x + bx) * 2;
             p[0] = s1;
             p[1] = s2;
         }

@@ -22,11 +22,16 @@ __device__ __forceinline__ Seed32 seed_split(u64 s) { return Seed32{(unsigned)s,
 __device__ __forceinline__ u64 seed_join(Seed32 s) { return (((u64)s.hi << 32) | s.lo) & LCG_MASK; }
 
 // x*A + c  (mod 2^64 in the low word, bits 32..47 valid in the high word); c stays a native
-// 64-bit value so the IMAD.WIDE addend needs no register-pair packing
+// 64-bit value so the IMAD.WIDE addend needs no register-pair packing.  Inline PTX on purpose:
+// left to the optimiser, a chain of these is re-associated into independent polynomials in the
+// seed with a dozen loop-carried constants -- twice the integer instructions (profiles/).
 __device__ __forceinline__ void mad48(unsigned xl, unsigned xh, u64 c, unsigned &rl, unsigned &rh) {
-    const u64 p = (u64)xl * A_LO + c;                  // IMAD.WIDE.U32 with 64-bit addend
-    rl = (unsigned)p;
-    rh = (unsigned)(p >> 32) + xl * A_HI + xh * A_LO;  // 2 x IMAD
+    u64 p;
+    unsigned ph, t;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(xl), "r"(A_LO), "l"(c));  // IMAD.WIDE.U32
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(rl), "=r"(ph) : "l"(p));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(xl), "r"(A_HI), "r"(ph));     // IMAD
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(rh) : "r"(xh), "r"(A_LO), "r"(t));     // IMAD
 }
 
 // One draw at the site whose constant is c = gid*A + B.  Returns u1 = t1>>16, u2 = t2>>16 (32 bits
@@ -37,8 +42,22 @@ __device__ __forceinline__ void site_draw(Seed32 &s, u64 c, unsigned &u1, unsign
     u1 = __funnelshift_r(t1l, t1h, 16);
     mad48(t1l, t1h, c, t2l, t2h);             // t2 = (t1+g)A + B = t1 A + c
     u2 = __funnelshift_r(t2l, t2h, 16);
-    s.lo = t2l + 0x80000000u;                 // t2 - 2^31
-    s.hi = t2h - (t2l < 0x80000000u ? 1u : 0u);
+    // t2 - 2^31 = t2 + 2^31 - 2^32: carry chain, 2 instructions
+    asm("add.cc.u32 %0, %2, 0x80000000;\n\taddc.u32 %1, %3, 0xffffffff;" : "=r"(s.lo), "=r"(s.hi) : "r"(t2l), "r"(t2h));
+}
+// c += A (next site's constant), kept in IMAD.WIDE form so that c lives in an aligned register
+// pair and feeds the next mad.wide addend without moves: c + A_LO (carry into the high word), +5.
+// `one` must be opaque to ptxas (see opaque_one): a literal 1 is strength-reduced to a carry-chain add
+// whose result is NOT an aligned pair, and every following mad.wide then splits into 4-5 instructions.
+__device__ __forceinline__ unsigned opaque_one() { return blockDim.x >> 8; }  // kernels here run 256..511 threads
+__device__ __forceinline__ u64 site_const_next(u64 c, unsigned one) {
+    u64 r;
+    unsigned lo, hi;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(one), "r"(A_LO), "l"(c));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(r));
+    hi += A_HI;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
 }
 __device__ __forceinline__ u64 site_const(u64 gid) { return gid * LCG_A + LCG_B; }
 

@@ -38,7 +38,7 @@ using namespace sq;
 
 namespace sq {
 
-constexpr int FW = 8;          // sites per finder strip
+constexpr int FW = 16;         // sites per finder strip
 constexpr int SERIES_CHUNK = SESSION_SERIES_MAX / 3;
 
 struct SlabState {
@@ -84,28 +84,62 @@ __device__ __noinline__ void finder_cold(u64 *found, u64 sm, u64 g0, int w) {
 
 // Integer-only scan of the draws at gids [g_from, g_hi): the first gid whose draw meets the
 // necessary condition of an event (lcg_event) under the base (bg, bs) -- "draws at gid >= bg
-// chain from seed bs".  ~12 integer instructions per site, no memory traffic.
+// chain from seed bs".  No memory traffic.  Both events are decidable from the SEED sequence z
+// (z' = ALPHA z + BETA g + GAMMA: one 48-bit multiply-add per site instead of the two of a draw):
+//   inf-retry  t1 < 2^16        => (t1 mod 2^32) < 2^16, and the low 32 bits of t1 = z A + c are one IMAD;
+//   `seed+=`   z < 2^31 && ...  => (z >> 16) < 2^15.
+// One 3-input min per site collects both filters (threshold 2^16); candidates (p ~ 2^-15 per site)
+// are decided exactly on a cold path.  The strip-to-strip advance of a thread is one affine map with
+// a fixed stride in 32-bit limbs, as in sq_march.cu.
+constexpr unsigned ALPHA_LO = (unsigned)LCG_ALPHA, ALPHA_HI = (unsigned)(LCG_ALPHA >> 32);
+
 __global__ void __launch_bounds__(256) find_events_kernel(u64 bs, u64 bg, u64 g_from, u64 g_hi, const JumpEntry *jump,
                                                           JumpEntry stride_jump, u64 *found) {
     const u64 nthreads = (u64)gridDim.x * blockDim.x;
     u64 g = g_from + ((u64)blockIdx.x * blockDim.x + threadIdx.x) * FW;
     if (g >= g_hi) return;
-    u64 s = lcg_seed_at(bs, bg, g - bg, jump);
+    const u64 stride = nthreads * FW;
+    Seed32 z = seed_split(lcg_seed_at(bs, bg, g - bg, jump));
+    const unsigned aDl = (unsigned)stride_jump.a, aDh = (unsigned)(stride_jump.a >> 32);
+    u64 ck = (LCG_BETA * g + LCG_GAMMA) * stride_jump.g0 + stride_jump.bg1;  // z(next strip) = alpha^D z + ck
+    u64 dck = LCG_BETA * stride * stride_jump.g0;
+    u64 K = LCG_BETA * g + LCG_GAMMA;                     // z(next site) = ALPHA z + K
+    u64 dK = LCG_BETA * stride;
+    unsigned clo = (unsigned)site_const(g);               // low limb of gid*A + B
+    unsigned dclo = (unsigned)(stride * LCG_A);
+    asm volatile("" : "+l"(dck), "+l"(dK), "+r"(dclo));
     for (;;) {
-        Seed32 s32 = seed_split(s);
-        u64 cg = site_const(g);
+        const Seed32 z0 = z;
         unsigned m = 0xFFFFFFFFu;
+        u64 Ke = K;
+        unsigned ce = clo;
 #pragma unroll
         for (int e = 0; e < FW; ++e) {
-            unsigned u1, u2;
-            site_draw(s32, cg, u1, u2);
-            cg += LCG_A;
-            m = min(min(m, u1), u2);  // VIMNMX3: u1 == 0 or u2 < 2^15 both imply m < 2^15
+            const unsigned t1l = z.lo * A_LO + ce;                  // t1 mod 2^32
+            const unsigned zs = __funnelshift_r(z.lo, z.hi, 16);    // z >> 16 (bits 16..47)
+            m = min(min(m, t1l), zs);
+            u64 p;
+            unsigned pl, ph, t;
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(z.lo), "r"(ALPHA_LO), "l"(Ke));
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(pl), "=r"(ph) : "l"(p));
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(z.lo), "r"(ALPHA_HI), "r"(ph));
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(z.hi) : "r"(z.hi), "r"(ALPHA_LO), "r"(t));
+            z.lo = pl;
+            Ke += LCG_BETA;
+            ce += A_LO;
         }
-        if (__builtin_expect(m < 32768u, 0)) finder_cold(found, s, g, (int)((g_hi - g < (u64)FW) ? g_hi - g : (u64)FW));
-        const u64 gn = g + nthreads * FW;
+        if (__builtin_expect(m < 65536u, 0))
+            finder_cold(found, seed_join(z0), g, (int)((g_hi - g < (u64)FW) ? g_hi - g : (u64)FW));
+        const u64 gn = g + stride;
         if (gn >= g_hi) break;
-        s = lcg_apply(stride_jump, s, g) & LCG_MASK;
+        {   // next strip of this thread: stride draws further
+            const u64 p = (u64)z0.lo * aDl + ck;
+            z.lo = (unsigned)p;
+            z.hi = (unsigned)(p >> 32) + z0.lo * aDh + z0.hi * aDl;
+        }
+        ck += dck;
+        K += dK;
+        clo += dclo;
         g = gn;
     }
 }
@@ -291,14 +325,19 @@ extern "C" int sq_slab_join(sq_ctx *c, sq_session *s) {
 static int resolve_step(sq_ctx *c, u64 S, std::vector<RebaseEntry> &entries, u64 &S_next) {
     SlabState *sl = c->slab;
     entries.clear();
-    u64 bg = 0, bs = S, from = sl->g_lo;
+    // The scan needs no field data, so every round's remaining range [from, V) is split evenly over
+    // ALL ranks (not by slab): the ranks below an event would otherwise idle while those above rescan.
+    const u64 Vg = (u64)c->V;
+    u64 bg = 0, bs = S, from = 0;
     std::vector<uint64_t> all((size_t)sl->nranks);
     for (;;) {
         uint64_t local = NO_EVENT;
-        if (from < sl->g_hi) {
+        const u64 per = ((Vg - from + (u64)sl->nranks - 1) / (u64)sl->nranks + FW - 1) / FW * FW;
+        const u64 lo = std::min(Vg, from + (u64)sl->rank * per), hi = std::min(Vg, lo + per);
+        if (lo < hi) {
             *sl->h_found = NO_EVENT;
             CK(cudaMemcpyAsync(sl->d_found, sl->h_found, sizeof(u64), cudaMemcpyHostToDevice, sl->fstream));
-            find_events_kernel<<<sl->fgrid, 256, 0, sl->fstream>>>(bs, bg, from, sl->g_hi, c->d_jump, sl->fstride, sl->d_found);
+            find_events_kernel<<<sl->fgrid, 256, 0, sl->fstream>>>(bs, bg, lo, hi, c->d_jump, sl->fstride, sl->d_found);
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(sl->h_found, sl->d_found, sizeof(u64), cudaMemcpyDeviceToHost, sl->fstream));
             CK(cudaStreamSynchronize(sl->fstream));
@@ -325,12 +364,9 @@ static int resolve_step(sq_ctx *c, u64 S, std::vector<RebaseEntry> &entries, u64
         entries.push_back(e);
         bg = g + 1;
         bs = h.seed_after;
-        // slabs entirely below the event are final; the event's own slab continues behind it;
-        // slabs above start over with the new base
-        from = std::max<u64>(g + 1, sl->g_lo);
+        from = g + 1;  // everything up to the event is final; the rest is scanned again under the new base
     }
     // the omega work-item's draw at gid V (tau_kernel.cl:103-110)
-    const u64 Vg = (u64)c->V;
     const u64 sV = sq_host_seed_before(c, entries, 0, S, Vg);
     u64 t1, t2;
     lcg_draw(sV, Vg, t1, t2);
@@ -392,6 +428,7 @@ int sq_slab_enqueue(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
             CK(cudaMemcpyAsync(c->l_rebase, entries.data(), sizeof(RebaseEntry) * entries.size(), cudaMemcpyHostToDevice, c->stream));
         LatticeArgs A = sq_lattice_args(c, dtau, k);
         A.n_rebase = (int)entries.size();
+        sq_fill_rebase_inline(A, entries.data(), A.n_rebase);
         A.wrap_time = 0;
         const unsigned Tw = T0 + (unsigned)k, Tp = Tw + 1u;
         const int pw = (int)(Tw & 1u), pp = (int)(Tp & 1u);
@@ -409,7 +446,7 @@ int sq_slab_enqueue(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
         A.push_count = sl->d_count;
         A.slab_error = sl->d_error;
         if (c->timing && (rc = sq_timing_mark(c))) return rc;
-        CK(launch_lattice_step(A, p.real, p.math, c->ctas_per_slice, c->stream));
+        if ((rc = sq_launch_update(c, A))) return rc;
         if (c->timing && (rc = sq_timing_mark(c))) return rc;
         c->launches++;
         if (A.partials) {

@@ -17,6 +17,7 @@ SQ_MATH_ACCURATE, SQ_MATH_FAST = 0, 1
 SQ_POT_HARMONIC, SQ_POT_DOUBLEWELL, SQ_POT_PHI4 = 0, 3, 4
 SQ_FLAG_NO_OBSERVABLES = 1
 SQ_FLAG_FORCE_STREAMING = 2
+SQ_FLAG_GENERIC_KERNEL = 4
 
 
 class SqError(RuntimeError):
@@ -51,7 +52,8 @@ class SqRngEntry(C.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(PKG, "libsq.so")
+    # SQ_LIBRARY: tuning builds of the same library (tools/); the product is libsq.so
+    return os.environ.get("SQ_LIBRARY") or os.path.join(PKG, "libsq.so")
 
 
 def build(force: bool = False) -> None:
