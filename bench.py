@@ -41,6 +41,9 @@ WORKLOADS = {
                desc="configs[2]: 4-D 64^4 fp32, 100 tau-steps per step"),
     "slab": dict(dims=(256, 256, 256, 32), real="f32", pot=0, m2=0.0, lam=0.0, dtau=0.01, loops=10,
                  desc="configs[3] per-GPU slab: 256^3 x 32 fp32 (x8 GPUs = 256^4)"),
+    # configs[4]: independent chains over a coupling grid; 512 chains per GPU (x8 GPUs = 4096)
+    "c5": dict(dims=(32, 32, 32, 32), real="f32", pot=4, m2=0.25, lam=0.5, dtau=0.01, loops=100, nchains=512,
+               desc="configs[4] per-GPU share: 512 independent 32^4 chains, lambda in linspace(0,1,64) x 8 seeds, 100 tau-steps per step"),
     # one lattice, slab-decomposed along the time axis over the N ranks (strong scaling)
     "c4": dict(dims=(256, 256, 256, 256), real="f32", pot=0, m2=0.0, lam=0.0, dtau=0.01, loops=10, ring=True,
                desc="configs[3]: 4-D 256^4 fp32, time slabs over N GPUs, halos over NVLink inside the update kernel"),
@@ -212,9 +215,17 @@ def main():
         args.no_e2e = True          # a 17 GB pinned host frame per step is not this workload's use
         args.no_cpu_baseline = True
     else:
+        nch = int(wl.get("nchains", 1))
+        if nch > 1:
+            args.no_e2e = True      # frame_host moves one lattice; the batch of chains stays resident
         ctx = sq.Context(dims, real=wl["real"], math=args.math, potential=wl["pot"], m2=wl["m2"], lam=wl["lam"],
-                         device=local, seed=1242608872 + rank)
-    nshare = 1 if ring else world   # lattices advanced by the job
+                         device=local, seed=1242608872 + rank, nchains=nch)
+        if nch > 1:  # lambda grid x seeds, chains block-distributed over the ranks
+            lams = np.linspace(0.0, 1.0, 64)
+            for k in range(nch):
+                g = rank * nch + k
+                ctx.set_chain(k, 1242608872 + g // 64, wl["m2"], float(lams[g % 64]))
+    nshare = (1 if ring else world) * int(wl.get("nchains", 1))   # lattices advanced by the job
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -239,8 +250,8 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         ctx.step_async(dtau, loops)
+        ctx.sync()          # RNG-event replays are enqueued in here: they belong to the step
         e1.record(stream)
-        ctx.sync()
         e1.synchronize()
         ms.append(e0.elapsed_time(e1))
     barrier()
@@ -260,7 +271,7 @@ def main():
     ctx.kernel_timing(False)
     peak, peak_src = peaks()
     bpu = BYTES_PER_UPDATE[wl["real"]]
-    Vloc = ctx.vlocal  # sites one launch of this rank's kernel updates
+    Vloc = ctx.vlocal * int(wl.get("nchains", 1))  # sites one launch of this rank's kernel updates
     units_per_launch = Vloc * loops / max(kn, 1)
     ach = units_per_launch * bpu / (kms / max(kn, 1) * 1e-3) / 1e9
     traffic, tnote = None, None
@@ -270,19 +281,21 @@ def main():
             t = json.load(open(tp)).get(name)
             # ncu capture of one launch, scaled to the tau-steps one launch covers in this run
             traffic = t["bytes_per_launch"] * (units_per_launch / Vloc / t["tau_steps_per_launch"]) \
-                if "lattice_step" in t["kernel"] else t["bytes_per_launch"]
+                if "lattice_" in t["kernel"] else t["bytes_per_launch"]
             tnote = t["source"]
         except Exception:
             traffic = None
     resident = len(dims) == 2 and wl["real"] == "f32" and dims[0] % 128 == 0 and dims[0] <= 1024 and dims[1] <= 8 * 148
+    kname = "resident2d_kernel" if resident else ("lattice_march_kernel" if len(dims) >= 3 and wl["real"] == "f32"
+                                                  else "lattice_step_kernel")
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": tnote,
-                "kernel": "resident2d_kernel" if resident else "lattice_step_kernel", "launches_timed": kn,
+                "kernel": kname, "launches_timed": kn,
                 "tau_steps_per_launch": units_per_launch / Vloc,
                 "avg_launch_us": 1e3 * kms / max(kn, 1), "bytes_per_site_update": bpu, "peak_source": peak_src,
                 "note": ("on-chip resident kernel: the 4 MiB lattice is read/written once per launch, so `achieved` "
                          "(algorithmic bytes / time) measures instruction efficiency against the HBM roofline"
-                         if resident else "streaming kernel; ncu: instruction-issue-bound (DESIGN.md section 5)")}
+                         if resident else "streaming kernel: issue slots, L1 wavefronts and HBM are all at 50-60 % (DESIGN.md section 5)")}
 
     # ---- end to end through host buffers -------------------------------------------------
     e2e = None

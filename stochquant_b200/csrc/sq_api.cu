@@ -102,7 +102,7 @@ extern "C" void sq_free(sq_ctx *c) {
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
                     c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump,
-                    c->r_halo, c->r_error, c->r_hist_rows, c->r_hist_p2, c->r_step_sums};
+                    c->r_halo, c->r_error, c->r_progress, c->r_ckpt, c->r_hist_rows, c->r_hist_p2, c->r_step_sums};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -278,6 +278,8 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
                 c->res_rows = rows;
                 if ((rc = dalloc(&c->r_halo, 2 * (size_t)nb * 2 * (size_t)L0))) return rc;
                 if ((rc = dalloc(&c->r_error, 1))) return rc;
+                if ((rc = dalloc(&c->r_progress, (size_t)nb))) return rc;
+                if ((rc = dalloc(&c->r_ckpt, 3 * (size_t)c->V))) return rc;
                 if ((rc = dalloc(&c->r_hist_rows, (size_t)RES_MAX_STEPS * (size_t)L1))) return rc;
                 if ((rc = dalloc(&c->r_hist_p2, (size_t)RES_MAX_STEPS * (size_t)nb))) return rc;
                 if ((rc = dalloc(&c->r_step_sums, (size_t)RES_MAX_STEPS * 2))) return rc;
@@ -472,6 +474,7 @@ static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     return SQ_OK;
 }
 
+static int enqueue_resident_welford(sq_ctx *c, int nsteps, int64_t runs0);
 static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     const sq_params &p = c->p;
     const LatticeArgs L = sq_lattice_args(c, dtau, 0);
@@ -510,6 +513,8 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     A.hist_p2 = c->r_hist_p2;
     A.nclamped = c->l_nclamped;
     A.error_flag = c->r_error;
+    A.ckpt = c->r_ckpt;
+    A.progress = c->r_progress;
     // per-chain couplings live in device arrays for the streaming kernel; the resident kernel is
     // single-chain and takes them by value: keep both in sync through sq_set_chain (host mirror)
     if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
@@ -517,6 +522,12 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     CK(launch_resident2d(A, p.math, c->res_nb, c->res_rows, strip_w, c->stream));
     if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     c->launches++;
+    return enqueue_resident_welford(c, nsteps, runs0);
+}
+
+// history of a resident launch -> running means, for its first `nsteps` steps
+static int enqueue_resident_welford(sq_ctx *c, int nsteps, int64_t runs0) {
+    const sq_params &p = c->p;
     WelfordArgs W{};
     W.nt = c->nt;
     W.nsteps = nsteps;
@@ -621,7 +632,34 @@ static int sync_lattice(sq_ctx *c) {
                 runs0 += n;
                 if (c->res_limit > 0) { c->res_limit = 0; c->force_stream = 1; }
             } else {
-                const int k = (int)(key >> KEY_STEP_SHIFT);
+                // The launch stopped early (sq_resident.cu): keep everything up to the last checkpoint
+                // that EVERY CTA has written and that lies before the event, redo only the rest.
+                int k = (int)(key >> KEY_STEP_SHIFT);
+                std::vector<unsigned> prog((size_t)c->res_nb);
+                CK(cudaMemcpy(prog.data(), c->r_progress, sizeof(unsigned) * prog.size(), cudaMemcpyDeviceToHost));
+                const int reached = (int)*std::min_element(prog.begin(), prog.end());
+                const int c0 = std::min(reached, k) / RES_CKPT * RES_CKPT;
+                if (c0 > 0) {
+                    const u64 none = NO_EVENT;
+                    CK(cudaMemcpy(c->l_event, &none, sizeof(u64), cudaMemcpyHostToDevice));
+                    key = NO_EVENT;  // (already cleared: skip the reset below)
+                    CK(cudaMemcpyAsync(c->l_field[c->cur], c->r_ckpt + (size_t)((c0 / RES_CKPT) % 3) * (size_t)c->V,
+                                       sizeof(float) * (size_t)c->V, cudaMemcpyDeviceToDevice, c->stream));
+                    u64 S;  // the step-start seed, c0 event-free steps on (what the kernel's omega thread does)
+                    CK(cudaMemcpy(&S, c->l_seeds[c->cur], sizeof(u64), cudaMemcpyDeviceToHost));
+                    const JumpEntry vj = jump_entry((u64)c->V);
+                    for (int i = 0; i < c0; ++i) {
+                        u64 t1, t2;
+                        lcg_draw(lcg_apply(vj, S, 0) & LCG_MASK, (u64)c->V, t1, t2);
+                        S = lcg_next_seed(t2);
+                    }
+                    CK(cudaMemcpy(c->l_seeds[c->cur], &S, sizeof(u64), cudaMemcpyHostToDevice));
+                    int rw = enqueue_resident_welford(c, c0, runs0);
+                    if (rw) return rw;
+                    done += c0;
+                    runs0 += c0;
+                    k -= c0;
+                }
                 if (k > 0) c->res_limit = k;
                 else c->force_stream = 1;
             }
@@ -647,6 +685,7 @@ static int sync_lattice(sq_ctx *c) {
                 e.ov_t1 = h.t1;
                 e.ov_t2 = h.t2;
                 e.chain = chain;
+                e.vseed = virtual_start_seed(e.seed, e.gid_start, c->h_jump.data());
                 if ((int)c->entries.size() >= MAX_REBASE) return SQ_ERR_INVALID;
                 c->entries.push_back(e);
                 c->nevents++;

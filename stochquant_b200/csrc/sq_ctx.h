@@ -72,7 +72,8 @@ struct sq_ctx {
     bool res_ok = false;
     int res_nb = 0, res_rows = 0;
     unsigned long long *r_halo = nullptr;
-    unsigned *r_error = nullptr;
+    unsigned *r_error = nullptr, *r_progress = nullptr;
+    float *r_ckpt = nullptr;  // [3][V] checkpoints of the resident kernel (RNG-event recovery)
     unsigned r_tag = 1;     // monotonic halo tag base (never reused, also across replays)
     double *r_hist_rows = nullptr, *r_hist_p2 = nullptr, *r_step_sums = nullptr;
     int res_limit = 0;      // >0: the next resident batch must stop after this many steps

@@ -45,6 +45,10 @@ struct RebaseEntry {
     u64 ov_t1, ov_t2;
     int chain;
     int pad;
+    // virtual step-start seed: the event-free chain from vseed at gid 0 reproduces every seed at
+    // gid >= gid_start (alpha is odd, so  alpha^g vseed + c(0,g) = seed  can be solved for vseed).
+    // Lets a kernel reuse its gid-0-based jump tables behind the entry.  Filled by sq_fill_vseed.
+    u64 vseed;
 };
 
 constexpr int RB_INLINE = 4;
@@ -147,7 +151,15 @@ struct ResidentArgs {
     double *hist_p2;     // [nsteps][nblocks] partial sums of phi^2
     unsigned long long *nclamped;
     unsigned *error_flag;
+    // RNG-event recovery: every RES_CKPT steps each CTA drops its band (the field BEFORE step n,
+    // n a multiple of RES_CKPT) into ckpt[(n / RES_CKPT) % 3]; a CTA that sees the event word raised
+    // stops and records how far it got.  The host resumes from the last checkpoint every CTA has
+    // written instead of from the start of the launch (CTA skew is bounded by the halo dependency:
+    // at most nblocks/2 steps, far less than 2 * RES_CKPT).
+    float *ckpt;          // [3][L1][L0]
+    unsigned *progress;   // [nblocks] steps completed by each CTA when it left
 };
+constexpr int RES_CKPT = 128;
 cudaError_t launch_resident2d(const ResidentArgs &A, int math, int nblocks, int rows_max, int strip_w, cudaStream_t st);
 
 struct WelfordArgs {

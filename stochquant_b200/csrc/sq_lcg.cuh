@@ -107,6 +107,15 @@ inline void build_jump_table(JumpEntry *tab /* JUMP_TABLE_ENTRIES */) {
     }
 }
 
+// start seed S' at gid 0 whose event-free chain passes through seed `bs` before the draw at gid bg
+inline u64 virtual_start_seed(u64 bs, u64 bg, const JumpEntry *tab) {
+    const u64 c0 = lcg_seed_at(0, 0, bg, tab);
+    const u64 a = (lcg_seed_at(1, 0, bg, tab) - c0) & LCG_MASK;  // alpha^bg, odd
+    u64 inv = a;                                                 // Newton: 3 -> 6 -> ... -> 96 bits
+    for (int i = 0; i < 5; ++i) inv *= 2 - a * inv;
+    return ((bs - c0) * inv) & LCG_MASK;
+}
+
 // literal host replay of tau_kernel.cl:269-284 without the floating-point part:
 // the do/while repeats exactly when t1>>16 == 0 (v1 == 0 -> log = -inf -> result inf).
 struct HostDraw {

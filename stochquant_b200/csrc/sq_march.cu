@@ -61,29 +61,134 @@ struct Draws {
 
 // generic draws of one strip under the step's replay entries (a strip that contains an entry's
 // gid_start or its overridden site): literal 64-bit chain with overrides, as in lattice_step_kernel
-__device__ __noinline__ Draws draws_slow(const LatticeArgs A, int chain, u64 s, u64 g0) {
+__device__ __noinline__ Draws draws_slow(const RebaseEntry *rebase, int n_rebase, u64 *event_key_ptr, int step_index, int chain,
+                                         u64 s, u64 g0) {
     Draws d;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         const u64 g = g0 + e;
         u64 t1, t2;
         bool overridden = false;
-        for (int j = 0; j < A.n_rebase; ++j)
-            if (A.rebase[j].chain == chain && A.rebase[j].gid_start == g) s = A.rebase[j].seed;
+        for (int j = 0; j < n_rebase; ++j)
+            if (rebase[j].chain == chain && rebase[j].gid_start == g) s = rebase[j].seed;
         lcg_draw(s, g, t1, t2);
-        for (int j = 0; j < A.n_rebase; ++j)
-            if (A.rebase[j].chain == chain && A.rebase[j].ov_gid == g) {
-                t1 = A.rebase[j].ov_t1;
-                t2 = A.rebase[j].ov_t2;
+        for (int j = 0; j < n_rebase; ++j)
+            if (rebase[j].chain == chain && rebase[j].ov_gid == g) {
+                t1 = rebase[j].ov_t1;
+                t2 = rebase[j].ov_t2;
                 overridden = true;
             }
         if (!overridden && lcg_event(s & LCG_MASK, t1, t2))
-            atomicMin((unsigned long long *)A.event_key, event_key(A.step_index, chain, g));
+            atomicMin((unsigned long long *)event_key_ptr, event_key(step_index, chain, g));
         s = lcg_next_seed(t2) & LCG_MASK;
         d.u1[e] = (unsigned)(t1 >> 16);
         d.u2[e] = (unsigned)(t2 >> 16);
     }
     return d;
+}
+
+// A whole strip on the rare path (a replay entry's first site or its overridden site lies inside it):
+// scalar code, same operations and roundings per site as the packed hot path.
+struct SlowIn {
+    const float *cur, *tm, *tp;
+    float *dst, *push0, *push1;
+    unsigned o, o_up1, o_dn1, o_up2, o_dn2, o_left, o_right;  // offsets inside the slice
+    u64 s, g0;
+    int chain, step_index, n_rebase;
+    const RebaseEntry *rebase;
+    u64 *event_key;
+    float c_lap, c_dt, m2, lam, k2;
+    double nscale;
+};
+struct SlowOut {
+    float a1, a2;
+    unsigned nclamp;
+};
+template <int MATH, int NDIM, int POT>
+__device__ __noinline__ SlowOut strip_slow(const SlowIn I) {
+    const Draws d = draws_slow(I.rebase, I.n_rebase, I.event_key, I.step_index, I.chain, I.s, I.g0);
+    const float4 c = *reinterpret_cast<const float4 *>(I.cur + I.o);
+    const float4 u1 = *reinterpret_cast<const float4 *>(I.cur + I.o_up1), d1 = *reinterpret_cast<const float4 *>(I.cur + I.o_dn1);
+    float4 u2 = make_float4(0, 0, 0, 0), d2 = u2;
+    if (NDIM >= 4) {
+        u2 = *reinterpret_cast<const float4 *>(I.cur + I.o_up2);
+        d2 = *reinterpret_cast<const float4 *>(I.cur + I.o_dn2);
+    }
+    const float4 tp = *reinterpret_cast<const float4 *>(I.tp + I.o), tm = *reinterpret_cast<const float4 *>(I.tm + I.o);
+    const float left = I.cur[I.o_left], right = I.cur[I.o_right];
+    const float cc[4] = {c.x, c.y, c.z, c.w}, xp[4] = {c.y, c.z, c.w, right}, xm[4] = {left, c.x, c.y, c.z};
+    const float nu1[4] = {u1.x, u1.y, u1.z, u1.w}, nd1[4] = {d1.x, d1.y, d1.z, d1.w}, nu2[4] = {u2.x, u2.y, u2.z, u2.w},
+                nd2[4] = {d2.x, d2.y, d2.z, d2.w}, ntp[4] = {tp.x, tp.y, tp.z, tp.w}, ntm[4] = {tm.x, tm.y, tm.z, tm.w};
+    const float kth = (float)(2.0 * 3.1415 / 4294967296.0);
+    SlowOut r;
+    r.a1 = 0.f;
+    r.a2 = 0.f;
+    r.nclamp = 0;
+    float out[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float phi = cc[e];
+        float sum = __fadd_rn(xp[e], xm[e]);
+        sum = __fadd_rn(sum, nu1[e]);
+        sum = __fadd_rn(sum, nd1[e]);
+        if (NDIM >= 4) {
+            sum = __fadd_rn(sum, nu2[e]);
+            sum = __fadd_rn(sum, nd2[e]);
+        }
+        sum = __fadd_rn(sum, ntp[e]);
+        sum = __fadd_rn(sum, ntm[e]);
+        float v = __fmaf_rn(I.c_lap, __fmaf_rn(-(float)(2 * NDIM), phi, sum), phi);
+        if (POT == 4) v = __fmaf_rn(-I.c_dt, __fmul_rn(phi, __fmaf_rn(I.lam, __fmul_rn(phi, phi), I.m2)), v);
+        else v = __fmaf_rn(-2.0f * I.c_dt, phi, v);
+        if (MATH == 1) {
+            const float a = __fmul_rn(__uint2float_rn(d.u1[e]), 2.3283064365386963e-10f);
+            const float t = __fmul_rn(lg2_approx(a), I.k2);
+            const float th = __fmaf_rn(__uint2float_rn(d.u2[e]), kth, -3.14159265358979f);
+            v = __fmaf_rn(-__cosf(th), sqrt_approx(fabsf(t)), v);
+        } else {
+            v = __fadd_rn(v, (float)__dmul_rn(I.nscale, noise_accurate((u64)d.u1[e] << 16, (u64)d.u2[e] << 16)));
+        }
+        r.nclamp += (fabsf(v) <= 1000.0f) ? 0u : 1u;
+        out[e] = (v < 1000.0f) ? ((v > -1000.0f) ? v : -1000.0f) : 1000.0f;
+        r.a1 = __fadd_rn(r.a1, phi);
+        r.a2 = __fmaf_rn(phi, phi, r.a2);
+    }
+    const float4 res = make_float4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<float4 *>(I.dst + I.o) = res;
+    if (I.push0) *reinterpret_cast<float4 *>(I.push0 + I.o) = res;
+    if (I.push1) *reinterpret_cast<float4 *>(I.push1 + I.o) = res;
+    return r;
+}
+
+// Replay entries (REBASE): where does a strip stand relative to the step's (sorted) entries?  Every
+// entry carries a virtual step-start seed (RebaseEntry::vseed) under which the kernel's ordinary
+// gid-0-based jump tables and row recurrence stay valid behind it, so the hot loop only watches the
+// distance to the thread's NEXT entry; this runs once per thread and when an entry is reached.
+struct Rebased {
+    u64 S_eff;       // step-start seed whose event-free chain is valid at this strip
+    unsigned cnt;    // entries at or before the strip
+    unsigned nxt32;  // slice-relative offset of the next entry behind this strip (0x7FFFFFFF: none in this slice)
+    bool slow;       // an entry's gid_start or overridden site (= gid_start - 1) lies inside the strip
+};
+__device__ __forceinline__ Rebased rebase_eval(const RebaseEntry *rebase, int n_rebase, int chain, u64 S, u64 g0, u64 gslice,
+                                               unsigned vs) {
+    Rebased r;
+    r.S_eff = S;
+    r.cnt = 0;
+    r.slow = false;
+    u64 nxt = ~0ULL, bg = 0;
+    for (int j = 0; j < n_rebase; ++j) {
+        const u64 gs = rebase[j].gid_start;
+        if (rebase[j].chain != chain) continue;
+        if (gs <= g0) {
+            r.cnt++;
+            if (gs >= bg) { bg = gs; r.S_eff = rebase[j].vseed; }
+        }
+        r.slow |= (gs - g0 <= 4ULL);
+        if (gs > g0 + 4 && gs < nxt) nxt = gs;
+    }
+    r.nxt32 = (nxt - gslice < (u64)vs) ? (unsigned)(nxt - gslice) : 0x7FFFFFFFu;
+    return r;
 }
 
 struct Clamped {
@@ -110,7 +215,7 @@ __device__ __noinline__ Clamped clamp_cold(float a, float b, float c, float d) {
 #define MARCH_MINB 4
 #endif
 template <int MATH, int NDIM, int POT, bool REBASE>
-__global__ void __launch_bounds__(256, MARCH_MINB) lattice_march_kernel(const LatticeArgs A) {
+__global__ void __launch_bounds__(256, REBASE ? 3 : MARCH_MINB) lattice_march_kernel(const LatticeArgs A) {
     if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;  // an earlier launch must be replayed
     const int chain = blockIdx.z;
     int tl;
@@ -167,14 +272,21 @@ __global__ void __launch_bounds__(256, MARCH_MINB) lattice_march_kernel(const La
     const u64 S = A.seed_in[chain];
     unsigned o = r_start * L0 + x0;  // offset of the current strip inside the slice
     u64 g0 = gslice + o;
-    u64 s;
     unsigned cnt_prev = 0, nxt32 = 0x7FFFFFFFu;
-    if (!REBASE) {
-        const u64 s_sl = lcg_apply(A.slice_jump[tl], S, 0) & LCG_MASK;
+    u64 S_eff = S;
+    if (REBASE) {
+        const Rebased rb = rebase_eval(A.rebase, A.n_rebase, chain, S, g0, gslice, (unsigned)vs);
+        S_eff = rb.S_eff;
+        cnt_prev = rb.cnt;
+        nxt32 = rb.slow ? o : rb.nxt32;  // an entry inside the first strip: take the rare path at k == 0
+    }
+    // three precomputed jumps from gid 0: slice start, CTA's first row, this thread's first strip
+    const u64 g_cta = gslice + (u64)bx * rows_per_cta * L0;
+    u64 s;
+    {
+        const u64 s_sl = lcg_apply(A.slice_jump[tl], S_eff, 0) & LCG_MASK;
         const u64 s_cta = lcg_apply(A.cta_jump[bx], s_sl, gslice) & LCG_MASK;
-        s = lcg_apply(A.thr_jump[threadIdx.x], s_cta, gslice + (u64)bx * rows_per_cta * L0) & LCG_MASK;
-    } else {
-        s = 0;  // set at k == 0 below
+        s = lcg_apply(A.thr_jump[threadIdx.x], s_cta, g_cta) & LCG_MASK;
     }
     const unsigned aDl = (unsigned)A.row_jump.a, aDh = (unsigned)(A.row_jump.a >> 32);
     u64 ck = (LCG_BETA * g0 + LCG_GAMMA) * A.row_jump.g0 + A.row_jump.bg1;  // s(next row) = alpha^L0 s + ck
@@ -201,7 +313,10 @@ __global__ void __launch_bounds__(256, MARCH_MINB) lattice_march_kernel(const La
     pair_t ACC1 = 0, ACC2 = 0;  // (+0.0f, +0.0f)
     unsigned nclamp = 0;
 
-    for (unsigned k = 0; k < R; ++k) {
+    unsigned k = 0;
+    for (;;) {
+    // ---- hot inner loop: strips until the thread is done or (REBASE) reaches a replay entry -----
+    for (; k < R && (!REBASE || (int)(nxt32 - o) > 4); ++k) {
         const unsigned x1 = x1s + k;
         // ---- loads: everything is cur/tm/tp + 32-bit offset ----------------------------------------
         const unsigned d_up1 = (x1 + 1 == L1) ? 0u - row_wrap : L0;
@@ -219,46 +334,12 @@ __global__ void __launch_bounds__(256, MARCH_MINB) lattice_march_kernel(const La
         const float left = cur[(unsigned)(o + d_left)];
         const float right = cur[(unsigned)(o + d_right)];
 
-        // ---- seed of this strip under replay entries ---------------------------------------------
-        // Entries are sorted by gid and a thread visits its strips in increasing gid, so it only has
-        // to watch the distance to the NEXT entry (32-bit, relative to the slice): two instructions
-        // per strip.  Reaching one (rare) re-evaluates the base with the full 64-bit logic.
-        bool slow = false;
-        if (REBASE) {
-            if (k == 0 || (int)(nxt32 - o) <= 4) {
-                unsigned cnt = 0;
-                u64 nxt = ~0ULL;
-                for (int j = 0; j < A.n_rebase; ++j) {
-                    const u64 gs = (A.n_rebase <= RB_INLINE) ? A.rb_gid[j & (RB_INLINE - 1)] : A.rebase[j].gid_start;
-                    const int ch = (A.n_rebase <= RB_INLINE) ? A.rb_chain[j & (RB_INLINE - 1)] : A.rebase[j].chain;
-                    if (ch != chain) continue;
-                    cnt += (gs <= g0) ? 1u : 0u;
-                    slow |= (gs - g0 <= 4ULL);  // gid_start or ov_gid (= gid_start-1) inside this strip
-                    if (gs > g0 + 4 && gs < nxt) nxt = gs;
-                }
-                // beyond this slice (or none): never reached by (int)(nxt32 - o) <= 4
-                nxt32 = (nxt - gslice < (u64)vs) ? (unsigned)(nxt - gslice) : 0x7FFFFFFFu;
-                if (k == 0 || cnt != cnt_prev) {  // (re)base: table jump from the applicable entry
-                    u64 bg, bs;
-                    rebase_lookup(A, chain, S, g0, bg, bs);
-                    s32 = seed_split(lcg_seed_at(bs, bg, g0 - bg, A.jump));
-                }
-                cnt_prev = cnt;
-            }
-        }
         const Seed32 s_strip = s32;
 
         // ---- draws -----------------------------------------------------------------------------------
         unsigned u1[4], u2[4];
         unsigned umin = 0xFFFFFFFFu;
-        if (REBASE && slow) {
-            const Draws d = draws_slow(A, chain, seed_join(s32), g0);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                u1[e] = d.u1[e];
-                u2[e] = d.u2[e];
-            }
-        } else {
+        {
             u64 c = cg;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -360,6 +441,60 @@ __global__ void __launch_bounds__(256, MARCH_MINB) lattice_march_kernel(const La
         cg += dcg;
         g0 += L0;
         o += L0;
+    }
+    if (!REBASE || k >= R) break;
+        // ---- seed of this strip under replay entries ---------------------------------------------
+        // Entries are sorted by gid and a thread visits its strips in increasing gid, so it only has
+        // to watch the distance to the NEXT entry (32-bit, relative to the slice): two instructions
+        // per strip.  Reaching one (rare) re-evaluates the base with the full 64-bit logic.
+        if (REBASE) {
+            {   // an entry lies at or before strip k
+                const unsigned x1 = x1s + k;
+                // (everything it needs is re-derived here rather than kept live across the hot loop)
+                const u64 gsl = (u64)(A.slab_t0 + tl) * (u64)A.vslice;
+                const Rebased rb = rebase_eval(A.rebase, A.n_rebase, chain, A.seed_in[chain], g0, gsl, (unsigned)A.vslice);
+                nxt32 = rb.nxt32;
+                if (rb.cnt != cnt_prev) {  // new base: the thread's first strip under the new start seed, k rows down
+                    cnt_prev = rb.cnt;
+                    const u64 gc = gsl + (u64)bx * rows_per_cta * L0;
+                    const u64 s_sl = lcg_apply(A.slice_jump[tl], rb.S_eff, 0) & LCG_MASK;
+                    const u64 s_cta = lcg_apply(A.cta_jump[bx], s_sl, gsl) & LCG_MASK;
+                    Seed32 t = seed_split(lcg_apply(A.thr_jump[threadIdx.x], s_cta, gc) & LCG_MASK);
+                    u64 cj = (LCG_BETA * (g0 - (u64)k * L0) + LCG_GAMMA) * A.row_jump.g0 + A.row_jump.bg1;
+                    for (unsigned j = 0; j < k; ++j) {
+                        const u64 p = (u64)t.lo * aDl + cj;
+                        t.hi = (unsigned)(p >> 32) + t.lo * aDh + t.hi * aDl;
+                        t.lo = (unsigned)p;
+                        cj += dck;
+                    }
+                    s32 = t;
+                }
+                if (rb.slow) {  // the whole strip out of line; the row recurrence is void behind an entry
+                    SlowIn I;
+                    I.cur = cur; I.tm = tm; I.tp = tp; I.dst = dst;
+                    I.push0 = push_lo ? (float *)A.push_ghost[0] : nullptr;
+                    I.push1 = push_hi ? (float *)A.push_ghost[1] : nullptr;
+                    I.o = o;
+                    I.o_up1 = o + ((x1 + 1 == L1) ? 0u - row_wrap : L0);
+                    I.o_dn1 = o + ((x1 == 0) ? row_wrap : 0u - L0);
+                    I.o_up2 = o + d_up2; I.o_dn2 = o + d_dn2; I.o_left = o + d_left; I.o_right = o + d_right;
+                    I.s = seed_join(s32); I.g0 = g0;
+                    I.chain = chain; I.step_index = A.step_index; I.n_rebase = A.n_rebase;
+                    I.rebase = A.rebase; I.event_key = A.event_key;
+                    I.c_lap = c_lap; I.c_dt = c_dt; I.m2 = m2; I.lam = lam; I.k2 = A.k2_f; I.nscale = A.nscale;
+                    const SlowOut so = strip_slow<MATH, NDIM, POT>(I);
+                    ACC1 = add2(ACC1, pk(so.a1, 0.f));
+                    ACC2 = add2(ACC2, pk(so.a2, 0.f));
+                    nclamp += so.nclamp;
+                    nxt32 = o + L0;  // re-evaluate at the next strip (new base)
+                    ck += dck_;
+                    cg += dcg;
+                    g0 += L0;
+                    o += L0;
+                    ++k;
+                }
+            }
+        }
     }
 
     if (push_lo || push_hi) {  // last CTA of the slice: everything is out, raise the neighbour's flag

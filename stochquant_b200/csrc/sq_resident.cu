@@ -124,6 +124,22 @@ struct alignas(4 * W) RowPack {
     float v[W];
 };
 
+// checkpoint of a thread's band, out of line (by value: the hot loop's registers stay untouched)
+template <int N>
+struct Band {
+    float v[N];
+};
+template <int NR, int W>
+__device__ __noinline__ void checkpoint_cold(float *dst, int L0, const Band<NR * W> bd) {
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        RowPack<W> v;
+#pragma unroll
+        for (int e = 0; e < W; ++e) v.v[e] = bd.v[k * W + e];
+        *reinterpret_cast<RowPack<W> *>(dst + (size_t)k * L0) = v;
+    }
+}
+
 template <int NR, int MATH, int POT, int W, int TT>
 __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, float *smem) {
     const int T = TT ? TT : (int)blockDim.x;
@@ -192,8 +208,25 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
     const int tl = (t == 0) ? T - 1 : t - 1, tr = (t + 1 == T) ? 0 : t + 1;
     unsigned myclamp = 0;
 
-    for (int n = 0; n < A.nsteps; ++n) {
+    __shared__ unsigned s_abort;
+    if (t == 0) s_abort = 0;
+    u64 ek = NO_EVENT;  // thread 0: the event word as read one step ago (the load is never waited for)
+    int n = 0;
+    for (; n < A.nsteps; ++n) {
         const int eb = n & 1;
+        // ---- event recovery: checkpoint, early exit -------------------------------------------
+        if (__builtin_expect((n & (RES_CKPT - 1)) == 0 && n > 0, 0)) {
+            Band<NR * W> bd;
+#pragma unroll
+            for (int k = 0; k < NR; ++k)
+#pragma unroll
+                for (int e = 0; e < W; ++e) bd.v[k * W + e] = phi[k][e];
+            checkpoint_cold<NR, W>(A.ckpt + (size_t)((n / RES_CKPT) % 3) * (size_t)A.L1 * L0 + (size_t)r0 * L0 + W * t, L0, bd);
+        }
+        if (t == 0) {
+            if (ek != NO_EVENT) s_abort = 1;
+            ek = *((volatile const u64 *)A.event_key);
+        }
         float *rs = rs_all + (size_t)eb * (NR + 1) * T;  // double-buffered: last step's is being reduced
         float p2 = 0.f;
         // ---- one row: draws + update; returns the new values in out[] -----------------------
@@ -326,6 +359,7 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
         }
         rs[NR * T + t] = p2;
         __syncthreads();
+        if (s_abort) break;  // an RNG event somewhere: this launch will be resumed from a checkpoint
 
         // ---- per-row sums: warp w reduces row w (and the phi^2 column) ---------------------
         {
@@ -355,6 +389,8 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
         }
     }
 
+    if (t == 0) A.progress[b] = (unsigned)n;
+    if (n < A.nsteps) return;  // aborted: the output buffer is not needed
     // ---- write the band back ------------------------------------------------------------------
 #pragma unroll
     for (int k = 0; k < NR; ++k) {

@@ -361,6 +361,7 @@ static int resolve_step(sq_ctx *c, u64 S, std::vector<RebaseEntry> &entries, u64
         e.ov_t1 = h.t1;
         e.ov_t2 = h.t2;
         e.chain = 0;
+        e.vseed = virtual_start_seed(e.seed, e.gid_start, c->h_jump.data());
         entries.push_back(e);
         bg = g + 1;
         bs = h.seed_after;
@@ -380,6 +381,7 @@ static int resolve_step(sq_ctx *c, u64 S, std::vector<RebaseEntry> &entries, u64
         e.ov_t1 = h.t1;
         e.ov_t2 = h.t2;
         e.chain = 0;
+        e.vseed = virtual_start_seed(e.seed, e.gid_start, c->h_jump.data());
         entries.push_back(e);
     }
     S_next = h.seed_after;
