@@ -513,6 +513,8 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     A.hist_p2 = c->r_hist_p2;
     A.nclamped = c->l_nclamped;
     A.error_flag = c->r_error;
+    A.one = 1u;
+    for (int k = 0; k < 8; ++k) A.row_const[k] = (u64)k * (u64)p.dims[0] * LCG_A;
     A.ckpt = c->r_ckpt;
     A.progress = c->r_progress;
     // per-chain couplings live in device arrays for the streaming kernel; the resident kernel is

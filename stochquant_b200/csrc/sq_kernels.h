@@ -156,6 +156,8 @@ struct ResidentArgs {
     // stops and records how far it got.  The host resumes from the last checkpoint every CTA has
     // written instead of from the start of the launch (CTA skew is bounded by the halo dependency:
     // at most nblocks/2 steps, far less than 2 * RES_CKPT).
+    u64 row_const[8];     // k * L0 * A: the site constant gid*A+B of row k relative to the band's first row
+    unsigned one;         // 1, from the host: a multiplier ptxas cannot fold (sq_site.cuh: site_const_next)
     float *ckpt;          // [3][L1][L0]
     unsigned *progress;   // [nblocks] steps completed by each CTA when it left
 };

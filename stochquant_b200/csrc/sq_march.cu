@@ -16,44 +16,11 @@
 // Per-slice observables, the omega draw, replay entries (REBASE), L2 chunking and the slab ring's
 // halo protocol are those of the generic kernel.
 #include "sq_lattice_common.cuh"
+#include "sq_pair.cuh"
 
 namespace sq {
 
 namespace {
-
-typedef unsigned long long pair_t;  // two fp32 in one 64-bit register pair
-
-__device__ __forceinline__ pair_t pk(float lo, float hi) {
-    pair_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk(pair_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ pair_t add2(pair_t a, pair_t b) {
-    pair_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ pair_t mul2(pair_t a, pair_t b) {
-    pair_t r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ pair_t fma2(pair_t a, pair_t b, pair_t c) {
-    pair_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float sqrt_approx(float x) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 
 struct Draws {
     unsigned u1[4], u2[4];

@@ -23,6 +23,7 @@
 
 #include "sq_kernels.h"
 #include "sq_site.cuh"
+#include "sq_pair.cuh"
 
 namespace sq {
 
@@ -130,7 +131,8 @@ struct Band {
     float v[N];
 };
 template <int NR, int W>
-__device__ __noinline__ void checkpoint_cold(float *dst, int L0, const Band<NR * W> bd) {
+__device__ __noinline__ void checkpoint_cold(float *ckpt, int n, int L1, int L0, int r0, int t, const Band<NR * W> bd) {
+    float *dst = ckpt + (size_t)((n / RES_CKPT) % 3) * (size_t)L1 * L0 + (size_t)r0 * L0 + W * t;
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
         RowPack<W> v;
@@ -178,8 +180,9 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
     }
     const unsigned Pl = (unsigned)A.P, Ph = (unsigned)(A.P >> 32);
     // c = gid*A + B of the first site of row 0's strip; rows advance it by L0*A
-    const u64 c0 = site_const((u64)r0 * L0 + W * t);
-    const u64 rowA = (u64)L0 * LCG_A;
+    // (opaque: otherwise the 64-bit multiply gid*A+B is re-derived for every row of every step)
+    u64 c0 = site_const((u64)r0 * L0 + W * t);
+    asm volatile("" : "+l"(c0));
     // where this thread publishes its boundary-row words (parity 0 / 1) and reads its neighbours'
     unsigned long long *const pub0 = A.halo_ll + ((size_t)0 * nb + b) * 2 * L0 + W * t;
     unsigned long long *const pub1 = A.halo_ll + ((size_t)1 * nb + b) * 2 * L0 + W * t;
@@ -208,6 +211,14 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
     const int tl = (t == 0) ? T - 1 : t - 1, tr = (t + 1 == T) ? 0 : t + 1;
     unsigned myclamp = 0;
 
+    // constants of the packed pipeline (uniform operands of FFMA2 / FMUL2)
+    const pair_t K_m4 = pk(-4.0f, -4.0f), K_clap = pk(C.c_lap, C.c_lap), K_m2cdt = pk(-C.c_2dt, -C.c_2dt), K_mcdt = pk(-C.c_dt, -C.c_dt);
+    const pair_t K_lam = pk(C.lam, C.lam), K_m2 = pk(C.m2, C.m2), K_k2 = pk(C.k2, C.k2);
+    const pair_t K_2m32 = pk(2.3283064365386963e-10f, 2.3283064365386963e-10f);
+    const float kth = (float)(2.0 * 3.1415 / 4294967296.0);  // theta - pi = 2*3.1415 * u2 * 2^-32 - pi
+    const pair_t K_th = pk(kth, kth), K_mpi = pk(-3.14159265358979f, -3.14159265358979f);
+    const unsigned one = A.one;
+    (void)K_m4; (void)K_clap; (void)K_m2cdt; (void)K_mcdt; (void)K_lam; (void)K_m2; (void)K_k2; (void)K_2m32; (void)K_th; (void)K_mpi; (void)one;
     __shared__ unsigned s_abort;
     if (t == 0) s_abort = 0;
     u64 ek = NO_EVENT;  // thread 0: the event word as read one step ago (the load is never waited for)
@@ -221,7 +232,7 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
             for (int k = 0; k < NR; ++k)
 #pragma unroll
                 for (int e = 0; e < W; ++e) bd.v[k * W + e] = phi[k][e];
-            checkpoint_cold<NR, W>(A.ckpt + (size_t)((n / RES_CKPT) % 3) * (size_t)A.L1 * L0 + (size_t)r0 * L0 + W * t, L0, bd);
+            checkpoint_cold<NR, W>(A.ckpt, n, A.L1, L0, r0, t, bd);
         }
         if (t == 0) {
             if (ek != NO_EVENT) s_abort = 1;
@@ -229,20 +240,55 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
         }
         float *rs = rs_all + (size_t)eb * (NR + 1) * T;  // double-buffered: last step's is being reduced
         float p2 = 0.f;
+        pair_t P2 = 0;  // packed path: (sum phi^2 over even sites, over odd sites)
         // ---- one row: draws + update; returns the new values in out[] -----------------------
         auto do_row = [&](int k, const float *cur, const float *up, const float *dn, float *out) {
             const float left = edge[((eb * NR + k) * 2 + 1) * T + tl];
             const float right = edge[((eb * NR + k) * 2 + 0) * T + tr];
-            u64 c = c0 + (u64)k * rowA;
+            u64 c = c0 + A.row_const[k];  // constant-bank operand: 2 instructions
             const uint4 st = chain[k * T + t];
             Seed32 s{st.x, st.y};
             const Seed32 s_before = s;
-            float a = 0.f, amax = 0.f;
+            float a = 0.f;
             bool maybe = false;
+            if constexpr (W == 2 && MATH == 1) {
+                // packed pipeline (sq_pair.cuh): both sites of the strip per instruction; unclamped values
+                // are stored once proved in range, RNG events / clamp hits leave through one cold test
+                unsigned u1a, u2a, u1b, u2b;
+                site_draw_c(s, c, u1a, u2a);
+                c += LCG_A;
+                site_draw_c(s, c, u1b, u2b);
+                const unsigned um = min(min(min(u1a, u2a), u1b), u2b);  // u1 == 0 or u2 < 2^15 => um < 2^15
+                const float ca = cur[0], cb = cur[1];
+                const pair_t Cp = pk(ca, cb);
+                pair_t S = pk(__fadd_rn(cb, left), __fadd_rn(right, ca));  // phi(+0) + phi(-0)
+                S = add2(S, pk(up[0], up[1]));
+                S = add2(S, pk(dn[0], dn[1]));
+                pair_t V = fma2(K_clap, fma2(K_m4, Cp, S), Cp);
+                if (POT == 4) V = fma2(K_mcdt, mul2(Cp, fma2(K_lam, mul2(Cp, Cp), K_m2)), V);
+                else V = fma2(K_m2cdt, Cp, V);
+                float va, vb, l1a, l1b, ta, tb, tha, thb;
+                upk(V, va, vb);
+                upk(mul2(pk(__uint2float_rn(u1a), __uint2float_rn(u1b)), K_2m32), l1a, l1b);
+                upk(mul2(pk(lg2_approx(l1a), lg2_approx(l1b)), K_k2), ta, tb);
+                upk(fma2(pk(__uint2float_rn(u2a), __uint2float_rn(u2b)), K_th, K_mpi), tha, thb);
+                out[0] = __fmaf_rn(-__cosf(tha), sqrt_approx(fabsf(ta)), va);
+                out[1] = __fmaf_rn(-__cosf(thb), sqrt_approx(fabsf(tb)), vb);
+                a = __fadd_rn(ca, cb);
+                P2 = fma2(Cp, Cp, P2);
+                const float amax = fmaxf(fabsf(out[0]), fabsf(out[1]));
+                if (__builtin_expect((um < 32768u) | !(amax < 1000.0f), 0)) {
+                    maybe = um < 32768u;
+                    myclamp += (fabsf(out[0]) <= 1000.0f ? 0u : 1u) + (fabsf(out[1]) <= 1000.0f ? 0u : 1u);
+                    out[0] = (out[0] < 1000.0f) ? ((out[0] > -1000.0f) ? out[0] : -1000.0f) : 1000.0f;  // NaN -> +1000
+                    out[1] = (out[1] < 1000.0f) ? ((out[1] > -1000.0f) ? out[1] : -1000.0f) : 1000.0f;
+                }
+            } else {
+            float amax = 0.f;
 #pragma unroll
             for (int e = 0; e < W; ++e) {
                 unsigned u1, u2;
-                site_draw(s, c, u1, u2);
+                site_draw_c(s, c, u1, u2);
                 c += LCG_A;
                 maybe |= site_maybe_event(u1, u2);
                 const float p = cur[e];
@@ -257,6 +303,7 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
             // clamp hits (tau_kernel.cl:122-132) are counted on a cold path
             if (__builtin_expect(amax >= 1000.0f, 0))
                 myclamp += count_clamped_cold(out[0], out[1], W > 2 ? out[W - 2] : 0.f, W > 2 ? out[W - 1] : 0.f);
+            }
             rs[k * T + t] = a;
             if (__builtin_expect(maybe, 0))
                 strip_events_cold(A.event_key, A.step_index0 + n, seed_join(s_before), (u64)(r0 + k) * L0 + W * t, W);
@@ -357,6 +404,11 @@ __device__ __forceinline__ void resident_run(const ResidentArgs &A, int r0, floa
             edge[((nbuf * NR + k) * 2 + 0) * T + t] = phi[k][0];
             edge[((nbuf * NR + k) * 2 + 1) * T + t] = phi[k][W - 1];
         }
+        if constexpr (W == 2 && MATH == 1) {
+            float lo, hi;
+            upk(P2, lo, hi);
+            p2 = __fadd_rn(lo, hi);
+        }
         rs[NR * T + t] = p2;
         __syncthreads();
         if (s_abort) break;  // an RNG event somewhere: this launch will be resumed from a checkpoint
@@ -439,32 +491,47 @@ __global__ void __launch_bounds__(256) history_sums_kernel(const WelfordArgs A, 
 __global__ void __launch_bounds__(128) welford_history_kernel(const WelfordArgs A, const double *step_sums) {
     if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const double inv_vs = 1.0 / (double)A.vslice;  // vslice is a small integer: P exact enough (<=1 ulp)
+    // The recurrence is sequential in n, so only multiply-adds may sit on its dependent chain: the
+    // divisions by the counter and by the slice volume become multiplications by reciprocals that are
+    // computed off the chain (<= 1 ulp fp64 from the oracle's quotient; the parity tolerance on the
+    // running means is 1e-3).
+    const double inv_vs = 1.0 / (double)A.vslice;
     if (t < A.nt) {
         double x = A.slice_x[t], xx0 = A.slice_xx0[t], last = 0;
-#pragma unroll 4
-        for (int n = 0; n < A.nsteps; ++n) {
-            const double cnt = (double)(A.runs + n + 1);
-            last = A.hist_rows[(size_t)n * A.nt + t];
-            const double P = last / (double)A.vslice;
-            const double Pm = A.hist_rows[(size_t)n * A.nt + A.tmid] / (double)A.vslice;
-            xx0 = xx0 + (P * Pm - xx0) / cnt;
-            x = x + (P - x) / cnt;
+        // the loads do not depend on the recurrence: fetch 16 steps at a time so their latencies overlap
+        constexpr int B = 16;
+        for (int n0 = 0; n0 < A.nsteps; n0 += B) {
+            double h[B], hm[B], rc[B];
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                const int n = min(n0 + j, A.nsteps - 1);
+                h[j] = A.hist_rows[(size_t)n * A.nt + t];
+                hm[j] = A.hist_rows[(size_t)n * A.nt + A.tmid];
+                rc[j] = 1.0 / (double)(A.runs + n0 + j + 1);
+            }
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                if (n0 + j < A.nsteps) {
+                    last = h[j];
+                    const double P = last * inv_vs, Pm = hm[j] * inv_vs;
+                    xx0 = fma(fma(P, Pm, -xx0), rc[j], xx0);
+                    x = fma(P - x, rc[j], x);
+                }
+            }
         }
         A.slice_x[t] = x;
         A.slice_xx0[t] = xx0;
         A.slice_sum[t] = last;
     }
-    (void)inv_vs;
     if (t == A.nt) {  // one spare thread: running means of <phi>, <phi^2>
         double m1 = A.sums_mean[0], m2 = A.sums_mean[1], s1 = 0, s2 = 0;
-        const double vol = (double)A.vslice * (double)A.nt;
+        const double inv_vol = 1.0 / ((double)A.vslice * (double)A.nt);
         for (int n = 0; n < A.nsteps; ++n) {
             s1 = step_sums[2 * n];
             s2 = step_sums[2 * n + 1];
-            const double cnt = (double)(A.runs + n + 1);
-            m1 += (s1 / vol - m1) / cnt;
-            m2 += (s2 / vol - m2) / cnt;
+            const double rc = 1.0 / (double)(A.runs + n + 1);
+            m1 = fma(s1 * inv_vol - m1, rc, m1);
+            m2 = fma(s2 * inv_vol - m2, rc, m2);
         }
         A.sums[0] = s1;
         A.sums[1] = s2;
@@ -475,7 +542,7 @@ __global__ void __launch_bounds__(128) welford_history_kernel(const WelfordArgs 
 
 cudaError_t launch_welford_history(const WelfordArgs &A, double *step_sums, cudaStream_t stream) {
     history_sums_kernel<<<(A.nsteps + 7) / 8, 256, 0, stream>>>(A, step_sums);
-    welford_history_kernel<<<(A.nt + 1 + 127) / 128, 128, 0, stream>>>(A, step_sums);
+    welford_history_kernel<<<(A.nt + 1 + 31) / 32, 32, 0, stream>>>(A, step_sums);
     return cudaGetLastError();
 }
 

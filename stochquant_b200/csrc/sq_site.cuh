@@ -47,9 +47,27 @@ __device__ __forceinline__ void site_draw(Seed32 &s, u64 c, unsigned &u1, unsign
 }
 // c += A (next site's constant), kept in IMAD.WIDE form so that c lives in an aligned register
 // pair and feeds the next mad.wide addend without moves: c + A_LO (carry into the high word), +5.
+// The same two functions left to the compiler (the form the resident kernel's short 2-site chains
+// compile best from: 13 integer instructions per site there, against 25 with the PTX form above,
+// while a 4-site chain in this form is expanded into polynomials by the optimiser -- measured both ways).
+__device__ __forceinline__ void mad48_c(unsigned xl, unsigned xh, u64 c, unsigned &rl, unsigned &rh) {
+    const u64 p = (u64)xl * A_LO + c;                  // IMAD.WIDE.U32 with 64-bit addend
+    rl = (unsigned)p;
+    rh = (unsigned)(p >> 32) + xl * A_HI + xh * A_LO;  // 2 x IMAD
+}
+__device__ __forceinline__ void site_draw_c(Seed32 &s, u64 c, unsigned &u1, unsigned &u2) {
+    unsigned t1l, t1h, t2l, t2h;
+    mad48_c(s.lo, s.hi, c, t1l, t1h);
+    u1 = __funnelshift_r(t1l, t1h, 16);
+    mad48_c(t1l, t1h, c, t2l, t2h);
+    u2 = __funnelshift_r(t2l, t2h, 16);
+    s.lo = t2l + 0x80000000u;                 // t2 - 2^31
+    s.hi = t2h - (t2l < 0x80000000u ? 1u : 0u);
+}
+
 // `one` must be opaque to ptxas (see opaque_one): a literal 1 is strength-reduced to a carry-chain add
 // whose result is NOT an aligned pair, and every following mad.wide then splits into 4-5 instructions.
-__device__ __forceinline__ unsigned opaque_one() { return blockDim.x >> 8; }  // kernels here run 256..511 threads
+__device__ __forceinline__ unsigned opaque_one() { return blockDim.x >> 8; }  // ONLY for kernels launched with 256..511 threads
 __device__ __forceinline__ u64 site_const_next(u64 c, unsigned one) {
     u64 r;
     unsigned lo, hi;
