@@ -247,6 +247,7 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
             CK(cudaMalloc((void **)&c->l_thr_jump, sizeof(JumpEntry) * tj.size()));
             CK(cudaMemcpy(c->l_cta_jump, cj.data(), sizeof(JumpEntry) * cj.size(), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(c->l_thr_jump, tj.data(), sizeof(JumpEntry) * tj.size(), cudaMemcpyHostToDevice));
+
         }
     }
     std::vector<u64> seeds((size_t)p.nchains);
@@ -273,6 +274,7 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
             const int nb = (int)std::min<int64_t>(sms, L1);
             const int rows = (int)((L1 + nb - 1) / nb);
             if (rows <= RES_MAX_ROWS) {
+                CK(preload_lattice_step(p.real, p.math, p.ndim));  // the event-recovery path: see sq_lattice.cu
                 c->res_ok = true;
                 c->res_nb = nb;
                 c->res_rows = rows;
@@ -447,26 +449,26 @@ static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
         A.seed_out = c->l_seeds[b ^ 1];
         A.n_rebase = (k == 0) ? (int)c->entries.size() : 0;
         sq_fill_rebase_inline(A, c->entries.data(), A.n_rebase);
+        FinalizeArgs F{};
+        F.nt = c->nt;
+        F.nchains = p.nchains;
+        F.ctas_per_slice = c->ctas_per_slice;
+        F.tmid_local = (tmid >= p.slab_t0 && tmid < p.slab_t0 + c->nt) ? (int)(tmid - p.slab_t0) : -1;
+        F.vslice = c->vslice;
+        F.runs = runs0 + k;
+        F.partials = c->l_partials;
+        F.slice_sum = c->l_slice_sum;
+        F.slice_x = c->l_slice_x;
+        F.slice_xx0 = c->l_slice_xx0;
+        F.sums = c->l_sums;
+        F.sums_mean = c->l_sums_mean;
+        F.history = nullptr;
+        F.event_key = c->l_event;
         if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
         { int rl = sq_launch_update(c, A); if (rl) return rl; }
         if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
         c->launches++;
         if (A.partials) {
-            FinalizeArgs F{};
-            F.nt = c->nt;
-            F.nchains = p.nchains;
-            F.ctas_per_slice = c->ctas_per_slice;
-            F.tmid_local = (tmid >= p.slab_t0 && tmid < p.slab_t0 + c->nt) ? (int)(tmid - p.slab_t0) : -1;
-            F.vslice = c->vslice;
-            F.runs = runs0 + k;
-            F.partials = c->l_partials;
-            F.slice_sum = c->l_slice_sum;
-            F.slice_x = c->l_slice_x;
-            F.slice_xx0 = c->l_slice_xx0;
-            F.sums = c->l_sums;
-            F.sums_mean = c->l_sums_mean;
-            F.history = nullptr;
-            F.event_key = c->l_event;
             CK(launch_finalize(F, c->stream));
             c->launches++;
         }

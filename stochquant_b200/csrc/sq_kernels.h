@@ -110,6 +110,7 @@ struct LatticeArgs {
 };
 cudaError_t launch_lattice_step(const LatticeArgs &A, int real, int math, int ctas_per_slice,
                                 cudaStream_t stream);
+cudaError_t preload_lattice_step(int real, int math, int ndim);
 cudaError_t launch_lattice_march(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream);
 
 struct FinalizeArgs {

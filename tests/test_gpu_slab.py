@@ -113,14 +113,17 @@ def test_ring_equals_single_context(gpu_sq):
     assert maxabs(np.concatenate([r["slice_xx0"] for r in res]), m["slice_xx0"]) < 1e-12
 
 
-def test_two_process_ring_over_ipc(gpu_sq, oracle, tmp_path):
-    """One process per GPU, halo arenas mapped through CUDA IPC, NVLink peer stores: needs 2 GPUs."""
-    if gpu_sq.load().sq_device_count() < 2:
-        pytest.skip("needs two GPUs (gpurun --gpus 2)")
-    dims = (32, 16, 8, 20)
+def test_multi_process_ring_over_ipc(gpu_sq, oracle, tmp_path):
+    """One process per GPU (all GPUs of the box, up to 8), halo arenas mapped through CUDA IPC, NVLink
+    peer stores: needs >= 2 GPUs."""
+    ngpu = gpu_sq.load().sq_device_count()
+    if ngpu < 2:
+        pytest.skip("needs two or more GPUs (gpurun --gpus 2|4|8)")
+    nr = min(ngpu, 8)
+    dims = (32, 16, 8, 24)
     name = "p" + uuid.uuid4().hex[:12]
-    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "slab_worker.py"), name, str(r), "2",
-                               ",".join(map(str, dims)), str(tmp_path / f"r{r}.npz")]) for r in range(2)]
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "slab_worker.py"), name, str(r), str(nr),
+                               ",".join(map(str, dims)), str(tmp_path / f"r{r}.npz")]) for r in range(nr)]
     for p in procs:
         assert p.wait(300) == 0
     rng = np.random.default_rng(9)
@@ -128,7 +131,7 @@ def test_two_process_ring_over_ipc(gpu_sq, oracle, tmp_path):
     o = oracle.LatticeOracle(dims, real=oracle.F32, potential=4, m2=0.25, lam=0.5, phi0=phi0)
     o.step(DTAU, 25)
     res = []
-    for r, (t0, nt) in enumerate(split_slabs(dims[-1], 2)):
+    for r, (t0, nt) in enumerate(split_slabs(dims[-1], nr)):
         z = np.load(tmp_path / f"r{r}.npz")
         res.append({k: (z[k] if z[k].ndim else z[k].item()) for k in z.files} | {"t0": t0, "nt": nt})
     check_against_oracle(res, o, dims, ATOL[("f32", "accurate")], 50 * ATOL[("f32", "accurate")])
