@@ -274,3 +274,44 @@ def test_resident_event_later_step(gpu_sq, oracle):
     assert m["seed"] == o.seed and m["runs"] == 20
     assert maxabs(g.download(), o.field) < ATOL[("f32", "fast")]
     assert maxabs(m["slice_xx0"], o.slice_xx0) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json's other configs at full size (SURVEY.md 8(d) C3, C5, and C4's per-GPU slab)
+def test_full_size_c3_vs_oracle(gpu_sq, oracle):
+    """configs[2] at full size (64^4 fp32, cold start): step seed bit-exact vs the OpenMP oracle, field
+    parity after 3 steps, slice observables; the marching kernel is the one that runs."""
+    dims = (64, 64, 64, 64)
+    g, o = pair(gpu_sq, oracle, dims, "f32", "fast")
+    g.step(DTAU, 3)
+    o.step(DTAU, 3, omp=True)
+    m = g.measure()
+    assert m["seed"] == o.seed and m["runs"] == 3
+    d = np.abs(g.download().astype(np.float64) - o.field.astype(np.float64))
+    assert d.max() < ATOL[("f32", "fast")], d.max()
+    assert np.sqrt(np.mean(d ** 2)) < 1e-6
+    assert maxabs(m["slice_x"], o.slice_x) < 1e-4 and maxabs(m["slice_xx0"], o.slice_xx0) < 1e-4
+
+
+def test_c5_chain_grid_properties(gpu_sq, oracle):
+    """configs[4] shape (32^4 chains over a lambda grid, 64 of the 512-per-GPU share): a chain's result
+    depends only on its own (seed, lambda) -- identical to the same chain run alone -- and two sampled
+    chains match the oracle."""
+    dims, nch = (32, 32, 32, 32), 64
+    lams = np.linspace(0.0, 1.0, 64)
+    g = gpu_sq.Context(dims, real="f32", math="fast", potential=4, nchains=nch)
+    for k in range(nch):
+        g.set_chain(k, 1242608872 + k // 8, 0.25, float(lams[k]))
+    g.step(DTAU, 4)
+    _, _, seeds = g.measure_chains()
+    for k in (0, 37):
+        solo = gpu_sq.Context(dims, real="f32", math="fast", potential=4, m2=0.25, lam=float(lams[k]), seed=1242608872 + k // 8)
+        solo.step(DTAU, 4)
+        assert np.array_equal(g.download(chain=k), solo.download())
+        assert int(seeds[k]) == solo.measure()["seed"]
+        o = oracle.LatticeOracle(dims, real=oracle.F32, potential=4, m2=0.25, lam=float(lams[k]), seed=1242608872 + k // 8)
+        o.step(DTAU, 4, omp=True)
+        assert int(seeds[k]) == o.seed
+        assert maxabs(g.download(chain=k), o.field) < ATOL[("f32", "fast")]
+    # chains with the same seed but different couplings share the noise stream, not the field
+    assert int(seeds[0]) == int(seeds[7]) and not np.array_equal(g.download(chain=0), g.download(chain=7))

@@ -135,3 +135,20 @@ def test_multi_process_ring_over_ipc(gpu_sq, oracle, tmp_path):
         z = np.load(tmp_path / f"r{r}.npz")
         res.append({k: (z[k] if z[k].ndim else z[k].item()) for k in z.files} | {"t0": t0, "nt": nt})
     check_against_oracle(res, o, dims, ATOL[("f32", "accurate")], 50 * ATOL[("f32", "accurate")])
+
+
+def test_c4_slab_size_ring_equals_single_context(gpu_sq):
+    """configs[3] geometry at the per-GPU slab size of the 8-GPU run, halved in time to keep the test
+    short: 256^3 slices (67 MB each), 16 of them; a ring of two 8-slice slabs must reproduce the single
+    context bit for bit (same kernel, same stream), with RNG events (0.08 expected per step at this
+    volume) handled by two different mechanisms -- replay there, finder here."""
+    dims = (256, 256, 256, 16)
+    whole = gpu_sq.Context(dims, real="f32", math="fast")
+    whole.step(DTAU, 6)
+    ref = whole.download()
+    seed = whole.measure()["seed"]
+    whole.close()
+    res = ring_threads(gpu_sq, 2, dims, None, [6], real="f32", math="fast")
+    assert all(r["seed"] == seed for r in res)
+    got = np.concatenate([r["field"] for r in res])
+    assert np.array_equal(got, ref)
