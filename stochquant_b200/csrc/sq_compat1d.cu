@@ -27,13 +27,26 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+// a / b, correctly rounded, for a divisor whose correctly rounded reciprocal rb = __drcp_rn(b) is at
+// hand (every division of time_dev has a loop-invariant divisor: eta, eta^2, dt2, the running-mean
+// counter).  Markstein's correction: q = RN(a rb), r = a - b q (exact in one fma), q' = RN(q + r rb)
+// is RN(a/b) whenever nothing overflows and b's significand is not all ones -- three dependent FMAs
+// where __ddiv_rn is ~130 instructions on a GPU without a hardware fp64 divider.  Bit-identical
+// results; non-finite intermediates fall back to the library division.
+__device__ __noinline__ double ddiv_cold(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ double ddiv_by(double a, double b, double rb) {
+    const double q = __dmul_rn(a, rb);
+    if (__builtin_expect(!(fabs(q) < 1e300), 0)) return ddiv_cold(a, b);  // a real branch: a select would evaluate both
+    const double r = __fma_rn(-q, b, a);
+    return __fma_rn(r, rb, q);
+}
 __device__ __forceinline__ double absol(double a) { return (a <= 0) ? -a : a; }  // :259-267
 
 // clas(a, w, pot), tau_kernel.cl:215-226 / :184-189 / :201-205
 __device__ __forceinline__ double clas(double a, double w, int pot) {
     if (pot == 3) {
         // eta * (double)tanh((float)((double)sqrt((float)(2.*V0/m))*(t-t0)/eta)); sqrtf(4.f) == 2
-        const double arg = ddiv(dmul(2.0, dsub(a, w)), ETA);
+        const double arg = ddiv_by(dmul(2.0, dsub(a, w)), ETA, __drcp_rn(ETA));  // (constant-folded)
         return dmul(ETA, (double)tanhf((float)arg));
     }
     return 0.;
@@ -42,7 +55,8 @@ __device__ __forceinline__ double clas(double a, double w, int pot) {
 __device__ __forceinline__ double ddPot(double a, int pot) {
     if (pot == 3) {
         constexpr double ee = ETA * ETA;  // eta*eta, folded with one rounding like any C compiler
-        return ddiv(dsub(ddiv(dmul(dmul(12. * V0, a), a), ee), 4. * V0), ee);
+        const double ree = __drcp_rn(ee);  // (constant-folded)
+        return ddiv_by(dsub(ddiv_by(dmul(dmul(12. * V0, a), a), ee, ree), 4. * V0), ee, ree);
     }
     return 2.;
 }
@@ -110,6 +124,7 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
             }
         }
     }
+    const double r_dt2 = __drcp_rn(A.dt2);
     int cur = 0;  // sh_om index holding the current omega
     int j = 0;
     int unstable = 0;
@@ -119,6 +134,7 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
         const double Vl0 = sh_lrgVl;
         const double stale = nfp_s[E0];
         const double n_inv_den = (double)(A.runs + j + 1);  // (double)(*runs+j+1), :144
+        const double r_n = __drcp_rn(n_inv_den);
         const double fmid = f_s[midpt];
         const double clmid = clas(dmul((double)midpt, dt), om, pot);
 
@@ -204,7 +220,7 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
                 inner = dsub(dadd(f_s[i + 1], f_s[i - 1]), dmul(2., fi));
             }
             // f + m*dtau*inner/dt2 - ddPot(cl)*f*dtau + dw      (m = 1: m*dtau == dtau)
-            double nf = dadd(dsub(dadd(fi, ddiv(dmul(dtau, inner), A.dt2)),
+            double nf = dadd(dsub(dadd(fi, ddiv_by(dmul(dtau, inner), A.dt2, r_dt2)),
                                   dmul(dmul(ddPot(cl, pot), fi), dtau)),
                              dw);
             if (nf > 1000.) nf = 1000.;  // :122-132
@@ -217,8 +233,8 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
             d_s[i] = absol(dsub(dsub(nf, fi), dw));
             // :144-145, pre-update field
             const double path = dadd(fi, cl);
-            xx0_r[k] = dadd(xx0_r[k], ddiv(dsub(dmul(path, dadd(fmid, clmid)), xx0_r[k]), n_inv_den));
-            x_r[k] = dadd(x_r[k], ddiv(dsub(path, x_r[k]), n_inv_den));
+            xx0_r[k] = dadd(xx0_r[k], ddiv_by(dsub(dmul(path, dadd(fmid, clmid)), xx0_r[k]), n_inv_den, r_n));
+            x_r[k] = dadd(x_r[k], ddiv_by(dsub(path, x_r[k]), n_inv_den, r_n));
         }
         __syncthreads();
 
