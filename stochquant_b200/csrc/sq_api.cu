@@ -100,12 +100,17 @@ extern "C" void sq_free(sq_ctx *c) {
     void *ptrs[] = {c->d_jump, c->c_f, c->c_x, c->c_xx0, c->c_newf, c->c_newx, c->c_newxx0, c->c_omega,
                     c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps,
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
-                    c->l_event, c->l_rebase, c->l_partials, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
+                    c->l_event, c->l_rebase, c->l_partials, c->l_partials2, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
                     c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump,
                     c->r_halo, c->r_error, c->r_progress, c->r_ckpt, c->r_hist_rows, c->r_hist_p2, c->r_step_sums};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_upd[i]) cudaEventDestroy(c->ev_upd[i]);
+        if (c->ev_fin[i]) cudaEventDestroy(c->ev_fin[i]);
+    }
+    if (c->fin_stream) { cudaStreamSynchronize(c->fin_stream); cudaStreamDestroy(c->fin_stream); }
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -189,7 +194,8 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
         if (L0 % 4 == 0 && tpr >= 1 && tpr <= 256 && (tpr & (tpr - 1)) == 0) {
             const int64_t rg = 256 / tpr, nrows = c->vslice / L0;
             int best = 0;
-            for (int R = 16; R >= 1; R >>= 1) {
+            static const int force_R = getenv("SQ_MARCH_R") ? atoi(getenv("SQ_MARCH_R")) : 0;  // tuning knob
+            for (int R = force_R ? force_R : 16; R >= 1; R >>= 1) {
                 if (L1 % R != 0 || nrows % (rg * R) != 0) continue;
                 if (!best) best = R;  // the largest that fits ...
                 const int64_t ctas = nrows / (rg * R) * c->nt * p.nchains;
@@ -220,6 +226,12 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
     if ((rc = dalloc(&c->l_rebase, MAX_REBASE))) return rc;
     const size_t npart = (size_t)p.nchains * c->nt * c->ctas_per_slice * 2;
     if ((rc = dalloc(&c->l_partials, npart))) return rc;
+    if ((rc = dalloc(&c->l_partials2, npart))) return rc;
+    CK(cudaStreamCreateWithFlags(&c->fin_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&c->ev_upd[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_fin[i], cudaEventDisableTiming));
+    }
     const size_t nsl = (size_t)p.nchains * c->nt;
     if ((rc = dalloc(&c->l_slice_sum, nsl))) return rc;
     if ((rc = dalloc(&c->l_slice_x, nsl))) return rc;
@@ -435,6 +447,37 @@ int sq_launch_update(sq_ctx *c, const LatticeArgs &A) {
     return SQ_OK;
 }
 
+int sq_enqueue_step(sq_ctx *c, LatticeArgs &A, FinalizeArgs &F, int k) {
+    const int pb = k & 1;
+    if (A.partials) {
+        A.partials = pb ? c->l_partials2 : c->l_partials;
+        F.partials = A.partials;
+        // the finalize that read this buffer two steps ago must be done before it is overwritten
+        if (c->fin_pending > 1) CK(cudaStreamWaitEvent(c->stream, c->ev_fin[pb], 0));
+    }
+    if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
+    { int rl = sq_launch_update(c, A); if (rl) return rl; }
+    if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
+    c->launches++;
+    if (A.partials) {
+        CK(cudaEventRecord(c->ev_upd[pb], c->stream));
+        CK(cudaStreamWaitEvent(c->fin_stream, c->ev_upd[pb], 0));
+        CK(launch_finalize(F, c->fin_stream));
+        CK(cudaEventRecord(c->ev_fin[pb], c->fin_stream));
+        c->launches++;
+        c->fin_pending++;
+    }
+    return SQ_OK;
+}
+int sq_join_finalize(sq_ctx *c) {
+    if (c->fin_pending > 0) {
+        CK(cudaStreamWaitEvent(c->stream, c->ev_fin[0], 0));
+        if (c->fin_pending > 1) CK(cudaStreamWaitEvent(c->stream, c->ev_fin[1], 0));
+        c->fin_pending = 0;
+    }
+    return SQ_OK;
+}
+
 static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     const sq_params &p = c->p;
     LatticeArgs A = sq_lattice_args(c, dtau, 0);
@@ -464,16 +507,9 @@ static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
         F.sums_mean = c->l_sums_mean;
         F.history = nullptr;
         F.event_key = c->l_event;
-        if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
-        { int rl = sq_launch_update(c, A); if (rl) return rl; }
-        if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
-        c->launches++;
-        if (A.partials) {
-            CK(launch_finalize(F, c->stream));
-            c->launches++;
-        }
+        { int rs = sq_enqueue_step(c, A, F, k); if (rs) return rs; }
     }
-    return SQ_OK;
+    return sq_join_finalize(c);
 }
 
 static int enqueue_resident_welford(sq_ctx *c, int nsteps, int64_t runs0);

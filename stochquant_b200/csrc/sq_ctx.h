@@ -59,6 +59,12 @@ struct sq_ctx {
     double *l_partials = nullptr, *l_slice_sum = nullptr, *l_slice_x = nullptr, *l_slice_xx0 = nullptr,
            *l_sums = nullptr, *l_sums_mean = nullptr, *l_m2 = nullptr, *l_lam = nullptr, *l_redbuf = nullptr;
     unsigned long long *l_nclamped = nullptr;
+    // observables off the critical path: finalize(n) runs on a side stream while update(n+1) runs;
+    // the per-CTA partials are double-buffered, events order producer and consumer (sq_api.cu)
+    double *l_partials2 = nullptr;
+    cudaStream_t fin_stream = nullptr;
+    cudaEvent_t ev_upd[2] = {nullptr, nullptr}, ev_fin[2] = {nullptr, nullptr};
+    int fin_pending = 0;  // finalize launches of the current sequence not yet joined into `stream`
     int cur = 0;
     int nt = 0, ctas_per_slice = 1;
     int64_t vslice = 0, V = 0, vlocal = 0;
@@ -101,7 +107,10 @@ int sq_set_dev(sq_ctx *c);
 int sq_timing_mark(sq_ctx *c);
 int sq_timing_collect(sq_ctx *c, size_t valid);
 sq::LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k);
-int sq_launch_update(sq_ctx *c, const sq::LatticeArgs &A);  // generic or marching kernel
+int sq_launch_update(sq_ctx *c, const sq::LatticeArgs &A);
+// one step = update on `stream` + finalize on the side stream (k = step index within the sequence)
+int sq_enqueue_step(sq_ctx *c, sq::LatticeArgs &A, sq::FinalizeArgs &F, int k);
+int sq_join_finalize(sq_ctx *c);  // make `stream` wait for the side stream's outstanding finalizes  // generic or marching kernel
 void sq_fill_rebase_inline(sq::LatticeArgs &A, const sq::RebaseEntry *e, int n);
 // seed (full u64) before the draw at gid g of the step whose start seed is S, under `entries`
 sq::u64 sq_host_seed_before(const sq_ctx *c, const std::vector<sq::RebaseEntry> &entries, int chain, sq::u64 S, sq::u64 g);

@@ -447,33 +447,26 @@ int sq_slab_enqueue(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
         A.push_flag[1] = sl->flag(sl->peer[1], pp, 0);
         A.push_count = sl->d_count;
         A.slab_error = sl->d_error;
-        if (c->timing && (rc = sq_timing_mark(c))) return rc;
-        if ((rc = sq_launch_update(c, A))) return rc;
-        if (c->timing && (rc = sq_timing_mark(c))) return rc;
-        c->launches++;
-        if (A.partials) {
-            FinalizeArgs F{};
-            F.nt = nt;
-            F.nchains = 1;
-            F.ctas_per_slice = c->ctas_per_slice;
-            F.tmid_local = -1;
-            F.vslice = c->vslice;
-            F.runs = runs0 + k;
-            F.partials = c->l_partials;
-            F.slice_sum = c->l_slice_sum;
-            F.slice_x = c->l_slice_x;
-            F.slice_xx0 = c->l_slice_xx0;
-            F.sums = c->l_sums;
-            F.sums_mean = c->l_sums_mean;
-            F.history = sl->d_hist + (size_t)k * (size_t)(nt + 2);
-            F.event_key = c->l_event;
-            CK(launch_finalize(F, c->stream));
-            c->launches++;
-        }
+        FinalizeArgs F{};
+        F.nt = nt;
+        F.nchains = 1;
+        F.ctas_per_slice = c->ctas_per_slice;
+        F.tmid_local = -1;
+        F.vslice = c->vslice;
+        F.runs = runs0 + k;
+        F.partials = c->l_partials;
+        F.slice_sum = c->l_slice_sum;
+        F.slice_x = c->l_slice_x;
+        F.slice_xx0 = c->l_slice_xx0;
+        F.sums = c->l_sums;
+        F.sums_mean = c->l_sums_mean;
+        F.history = sl->d_hist + (size_t)k * (size_t)(nt + 2);
+        F.event_key = c->l_event;
+        if ((rc = sq_enqueue_step(c, A, F, k))) return rc;
         S = S_next;
     }
     sl->seed = S;
-    return SQ_OK;
+    return sq_join_finalize(c);
 }
 
 int sq_slab_finish(sq_ctx *c) {
