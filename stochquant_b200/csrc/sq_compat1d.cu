@@ -26,7 +26,6 @@ constexpr double V0 = 2.;   // tau_kernel.cl:21
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 // a / b, correctly rounded, for a divisor whose correctly rounded reciprocal rb = __drcp_rn(b) is at
 // hand (every division of time_dev has a loop-invariant divisor: eta, eta^2, dt2, the running-mean
 // counter).  Markstein's correction: q = RN(a rb), r = a - b q (exact in one fma), q' = RN(q + r rb)

@@ -59,7 +59,9 @@ SQ_HD u64 lcg_apply(const JumpEntry &e, u64 s, u64 g) {
 
 // seed before the draw at gid g+D given seed s before the draw at gid g (no events)
 SQ_HD u64 lcg_seed_at(u64 s, u64 g, u64 D, const JumpEntry *__restrict__ tab) {
+#ifdef __CUDA_ARCH__
 #pragma unroll
+#endif
     for (int L = 0; L < JUMP_LEVELS; ++L) {
         const unsigned j = (unsigned)(D >> (8 * L)) & 255u;
         if (j) {

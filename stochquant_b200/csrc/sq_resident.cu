@@ -29,20 +29,6 @@ namespace sq {
 
 namespace {
 
-__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ float4 ld_cg_f4(const float *p) {
-    float4 v;
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-
 // cold path: exact event test of the 4 draws of a strip (literal replay is the host's job)
 __device__ __noinline__ void strip_events_cold(u64 *event_key_ptr, int step, u64 sm, u64 g0, int w) {
     for (int e = 0; e < w; ++e) {
@@ -89,14 +75,6 @@ __device__ __forceinline__ float site_update(float phi, float nsum, unsigned u1,
 }
 
 }  // namespace
-
-__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 // 16-byte load of two {float bits, tag} words; each 64-bit element is a single-copy-atomic scalar
 __device__ __forceinline__ ulonglong2 ld_relaxed_ll(const unsigned long long *p) {

@@ -53,7 +53,6 @@ struct SlabState {
     cudaStream_t fstream = nullptr;
     u64 *d_found = nullptr, *h_found = nullptr;
     u64 seed = 0;      // host mirror of the step-start seed (full u64)
-    u64 g_lo = 0, g_hi = 0;
     int fgrid = 0;
     JumpEntry fstride{};
     double *d_hist = nullptr;
@@ -242,8 +241,6 @@ extern "C" int sq_slab_join(sq_ctx *c, sq_session *s) {
     sl->rank = me;
     sl->nranks = R;
     sl->seed = seed0;
-    sl->g_lo = (u64)p.slab_t0 * (u64)c->vslice;
-    sl->g_hi = sl->g_lo + (u64)c->vlocal;
     const int64_t tmid = p.dims[p.ndim - 1] / 2;
     for (int r = 0; r < R; ++r)
         if ((uint64_t)tmid >= all[(size_t)r * 6] && (uint64_t)tmid < all[(size_t)r * 6] + all[(size_t)r * 6 + 1]) sl->tmid_owner = r;
