@@ -196,7 +196,9 @@ uint64_t sq_lcg_jump(uint64_t seed, uint64_t gid0, uint64_t ndraws);
  *     session, so all ranks apply the same corrections and the stream stays bit-exact;
  *   - the running means of Phi(t)Phi(t_mid) use the mid slice's owner's per-step sums.
  * With a joined context sq_step / sq_step_async / sq_sync / sq_measure are COLLECTIVE: every
- * rank of the ring must make the same calls with the same dtau / nsteps / runs0. */
+ * rank of the ring must make the same calls with the same dtau / nsteps / runs0.
+ * One rank per GPU: several ranks of a ring on the SAME device work for small lattices (tests) but
+ * can starve each other once a rank's boundary CTAs alone fill the device. */
 typedef struct sq_session sq_session;
 /* name: unique per ring (no '/'); the segment is unlinked once every rank has attached */
 int sq_session_open(sq_session **out, const char *name, int rank, int nranks);
