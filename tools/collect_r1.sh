@@ -17,6 +17,6 @@ PY
 # ncu: launch list of the default bench command, then full captures of the dominant kernels
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2_$TAG.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu1.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:resident2d -s 3 -c 1 -o gpurun_out/prof_c2_resident_$TAG python bench.py --workload c2 --steps 1 --warmup 3 --loops 100 --no-cpu-baseline --no-e2e > gpurun_out/ncu2.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:lattice_march -s 40 -c 1 -o gpurun_out/prof_c3_march_$TAG python bench.py --workload c3 --steps 1 --warmup 3 --loops 20 --no-cpu-baseline --no-e2e > gpurun_out/ncu3.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:lattice_march -s 41 -c 1 -o gpurun_out/prof_c3_march_$TAG python bench.py --workload c3 --steps 1 --warmup 3 --loops 20 --no-cpu-baseline --no-e2e > gpurun_out/ncu3.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"lattice_march|find_events" -s 12 -c 3 -o gpurun_out/prof_c4s_ring_$TAG python bench.py --workload c4s --steps 1 --warmup 3 --loops 4 --no-cpu-baseline --no-e2e > gpurun_out/ncu4.log 2>&1
-tail -1 gpurun_out/ncu2.log gpurun_out/ncu3.log gpurun_out/ncu4.log
+for f in gpurun_out/ncu2.log gpurun_out/ncu3.log gpurun_out/ncu4.log; do tail -n 1 $f; done
