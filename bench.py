@@ -244,7 +244,9 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from slab_common import split_slabs
         slab = split_slabs(dims[-1], world)[rank]
-        sess = sq.Session(f"bench{os.environ.get('MASTER_PORT', os.getpid())}", rank, world)
+        # unique per launch (torchrun exports a run id): a crashed earlier run must not leave a segment we reuse
+        run_id = "".join(ch for ch in os.environ.get("TORCHELASTIC_RUN_ID", "") if ch.isalnum())[:24]
+        sess = sq.Session(f"bench{os.environ.get('MASTER_PORT', os.getpid())}{run_id}", rank, world)
         ctx = sq.Context(dims, real=wl["real"], math=args.math, potential=wl["pot"], m2=wl["m2"], lam=wl["lam"],
                          device=local, seed=1242608872, slab=slab)
         ctx.join(sess)
