@@ -6,7 +6,8 @@
  *
  * What changed underneath: the OpenCL context/queue/buffer/kernel-launch code
  * (:187-481, :504-554, :587-612) is gone; the frame loop calls the C-ABI of libsq
- * (include/sq.h): sq_init / sq_step(_async) / sq_measure / sq_free.  No tau_kernel.cl is
+ * (include/sq.h): sq_init / sq_frames (= sq_step + the controller of :504-545, on the device) /
+ * sq_measure / sq_free.  No tau_kernel.cl is
  * read from the working directory.  There is no CPU fallback: without a CUDA device the
  * program prints the libsq error and exits non-zero.
  *
@@ -40,7 +41,6 @@ int main(int argc, char **argv)
         return 1;
     }
     const int n = a.n;
-    const int mid = n / 2;
     double *f = (double *)calloc((size_t)n, sizeof(double));
     double *x = (double *)calloc((size_t)n, sizeof(double));
     double *xx0 = (double *)calloc((size_t)n, sizeof(double));
@@ -85,35 +85,36 @@ int main(int argc, char **argv)
     obs.x = x;
     obs.xx0 = xx0;
 
-    int runs = rec_sim_length, stab_cnt = 0;
-    for (int j = 0; j < a.frames; ++j) {
-        /* launch the frame, then format the previous frame's line while the GPU works:
-         * the reference prints after clFinish but before its read-backs (:483-501), i.e. the
-         * same (one frame old) xavg */
-        if ((rc = sq_step_async(ctx, dtau, a.loops, runs)) != SQ_OK) return fail_sq("sq_step", rc);
-        if (j % a.fps == 0) th_print_frame(stdout, n, xavg, dtau, j, a.frames);
-        int stable = 1;
-        if ((rc = sq_sync(ctx, &stable)) != SQ_OK) return fail_sq("sq_sync", rc);
-        if (stable == 1) {
-            if ((rc = sq_measure(ctx, &obs)) != SQ_OK) return fail_sq("sq_measure", rc);
-            omega = obs.omega;
-            for (int i = 0; i < n; ++i) xavg[i] = xx0[i] - x[i] * x[mid];
-            if (stab_cnt > 10) { /* :523-528 */
-                stab_cnt = 0;
-                dtau /= 0.950;
-            }
-            ++stab_cnt;
-            runs += a.loops;
-        } else { /* :533-545: shrink the step; libsq already rolled the frame back */
-            dtau *= 0.950;
-            stab_cnt = 0;
+    /* The frame loop of tauhost.c:479-560 with its controller (:504-545) on the device: frames run in
+     * batches with no host round trip in between (sq_frames); the host formats the lines afterwards.
+     * Line j shows the xavg of the last accepted frame before j and the step size frame j ran with,
+     * exactly what the reference prints between its clFinish and its read-backs (:483-501). */
+    int64_t runs = rec_sim_length;
+    int stab_cnt = 0;
+    if ((rc = sq_controller_set(ctx, dtau, runs, stab_cnt)) != SQ_OK) return fail_sq("sq_controller_set", rc);
+    sq_frame_rec recs[SQ_FRAMES_MAX];
+    double *xlog = (double *)malloc(sizeof(double) * (size_t)SQ_FRAMES_MAX * (size_t)n);
+    if (!xlog) return 3;
+    /* small batches first: the front-end shows progress while the step size is still settling */
+    for (int j = 0; j < a.frames;) {
+        int nb = a.frames - j;
+        const int cap = j < 64 ? 8 : SQ_FRAMES_MAX;
+        if (nb > cap) nb = cap;
+        if ((rc = sq_frames(ctx, nb, a.loops, recs, xlog)) != SQ_OK) return fail_sq("sq_frames", rc);
+        for (int k = 0; k < nb; ++k, ++j) {
+            if (j % a.fps == 0) th_print_frame(stdout, n, xavg, recs[k].dtau, j, a.frames);
+            if (recs[k].stable == 1) memcpy(xavg, xlog + (size_t)k * n, sizeof(double) * (size_t)n);
         }
         fflush(stdout);
     }
+    free(xlog);
+    if ((rc = sq_measure(ctx, &obs)) != SQ_OK) return fail_sq("sq_measure", rc); /* f, x, xx0, omega for the end file */
+    omega = obs.omega;
+    if ((rc = sq_controller_get(ctx, &dtau, &runs, &stab_cnt)) != SQ_OK) return fail_sq("sq_controller_get", rc);
 
     int status = 0;
     if (strcmp(a.end_file, "0") != 0) {
-        if (th_write_end_file(a.end_file, n, a.end_accuracy, xavg, xx0, x, f, omega, runs + rec_sim_length, dtau)) {
+        if (th_write_end_file(a.end_file, n, a.end_accuracy, xavg, xx0, x, f, omega, (int)runs + rec_sim_length, dtau)) {
             fprintf(stderr, "Failed to write to Output.\n");
             status = 1;
         }

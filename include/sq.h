@@ -134,6 +134,28 @@ int sq_measure(sq_ctx *ctx, sq_obs *out);
 /* Replaces tauhost.c:587-612. */
 void sq_free(sq_ctx *ctx);
 
+/* ---- frame controller on the device (COMPAT1D) ---------------------------
+ * The reference host decides after EVERY frame whether to keep it and how to change the step size
+ * (tauhost.c:504-545): one blocking read of `stable`, four read-backs, five re-uploads per frame.
+ * Here that logic runs in the frame kernel's epilogue, so a batch of frames needs no host round trip:
+ *   stable:   commit; every 11th consecutive stable frame dtau /= 0.95 (:523-528); runs += nsteps
+ *   unstable: roll back (seed, lrgEl, lrgVl keep their new values, :533-554); dtau *= 0.95
+ * and each frame logs what the host prints for it.  Results are bit-identical to driving sq_step
+ * frame by frame with the same rules (tests/test_gpu_compat1d.py::test_device_controller_*). */
+typedef struct sq_frame_rec {
+    double dtau;      /* step size the frame ran with (the value its stdout line shows, :495)  */
+    int32_t stable;   /* 1: committed, 0: rolled back                                          */
+    int32_t steps;    /* tau-steps executed (an unstable frame stops early, tau_kernel.cl:169) */
+} sq_frame_rec;
+#define SQ_FRAMES_MAX 64 /* frames per sq_frames call */
+/* state of the controller: dtau of the next frame, `runs` (tauhost.c:554), consecutive stable frames */
+int sq_controller_set(sq_ctx *ctx, double dtau, int64_t runs, int stab_cnt);
+int sq_controller_get(sq_ctx *ctx, double *dtau, int64_t *runs, int *stab_cnt);
+/* Run nframes (<= SQ_FRAMES_MAX) frames of nsteps tau-steps back to back.  recs: [nframes].
+ * xavg (NULL to skip): [nframes][N], row k = xx0[i]-x[i]*x[mid] after frame k if it was stable
+ * (tauhost.c:519-521), else untouched.  Synchronous. */
+int sq_frames(sq_ctx *ctx, int nframes, int nsteps, sq_frame_rec *recs, double *xavg);
+
 /* ---- support ----------------------------------------------------------------- */
 const char *sq_strerror(int code);
 const char *sq_last_cuda_error(void); /* text of the last CUDA failure, this thread */

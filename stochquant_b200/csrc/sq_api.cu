@@ -98,7 +98,7 @@ extern "C" void sq_free(sq_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     sq_slab_destroy(c);
     void *ptrs[] = {c->d_jump, c->c_f, c->c_x, c->c_xx0, c->c_newf, c->c_newx, c->c_newxx0, c->c_omega,
-                    c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps,
+                    c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps, c->c_ctl, c->c_log_rec, c->c_log_xavg,
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_partials2, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
                     c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump,
@@ -135,6 +135,9 @@ static int init_compat(sq_ctx *c, const double *f0, const double *x0, const doub
     if ((rc = dalloc(&c->c_stable, 1))) return rc;
     if ((rc = dalloc(&c->c_lrgEl, 1))) return rc;
     if ((rc = dalloc(&c->c_steps, 1))) return rc;
+    if ((rc = dalloc(&c->c_ctl, 1))) return rc;
+    if ((rc = dalloc(&c->c_log_rec, SQ_FRAMES_MAX))) return rc;
+    if ((rc = dalloc(&c->c_log_xavg, (size_t)SQ_FRAMES_MAX * (size_t)N))) return rc;
     const size_t nb = sizeof(double) * (size_t)N;
     // tauhost.c:177-183 + :319-334: new* start as copies of f/x/xx0
     if (f0) {
@@ -344,9 +347,16 @@ extern "C" int sq_init(sq_ctx **out, const sq_params *p, const double *f0, const
 }
 
 // ------------------------------------------------------------------- stepping -------------
-static int enqueue_compat(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
+static int enqueue_compat(sq_ctx *c, double dtau, int nsteps, int64_t runs0, bool controller = false) {
     const sq_params &p = c->p;
     Compat1DArgs A{};
+    if (controller) {
+        A.ctl = c->c_ctl;
+        A.log_rec = c->c_log_rec;
+        A.log_xavg = c->c_log_xavg;
+        A.log_cap = SQ_FRAMES_MAX;
+        A.noise_c = p.noise_c;
+    }
     A.N = (int)p.dims[0];
     A.loops = nsteps;
     A.potential = p.potential;
@@ -1028,5 +1038,61 @@ extern "C" uint64_t sq_lcg_jump(uint64_t seed, uint64_t gid0, uint64_t ndraws) {
 extern "C" int sq_slab_stats(sq_ctx *c, uint64_t *finder_scans, uint64_t *agree_rounds) {
     if (!c) return SQ_ERR_INVALID;
     sq_slab_stats_impl(c, finder_scans, agree_rounds);
+    return SQ_OK;
+}
+
+// ------------------------------------------------------------------- frame controller (f-3) --
+extern "C" int sq_controller_set(sq_ctx *c, double dtau, int64_t runs, int stab_cnt) {
+    if (!c || c->p.kernel != SQ_KERNEL_COMPAT1D || c->pending || !(dtau > 0)) return SQ_ERR_INVALID;
+    int rc = sq_set_dev(c);
+    if (rc) return rc;
+    Compat1DCtl h{};
+    h.dtau = dtau;
+    h.runs = runs;
+    h.stab_cnt = stab_cnt;
+    h.frame = 0;
+    c->c_frames_done = 0;
+    CK(cudaMemcpy(c->c_ctl, &h, sizeof h, cudaMemcpyHostToDevice));
+    return SQ_OK;
+}
+extern "C" int sq_controller_get(sq_ctx *c, double *dtau, int64_t *runs, int *stab_cnt) {
+    if (!c || c->p.kernel != SQ_KERNEL_COMPAT1D || c->pending) return SQ_ERR_INVALID;
+    int rc = sq_set_dev(c);
+    if (rc) return rc;
+    Compat1DCtl h{};
+    CK(cudaMemcpy(&h, c->c_ctl, sizeof h, cudaMemcpyDeviceToHost));
+    if (dtau) *dtau = h.dtau;
+    if (runs) *runs = h.runs;
+    if (stab_cnt) *stab_cnt = h.stab_cnt;
+    return SQ_OK;
+}
+extern "C" int sq_frames(sq_ctx *c, int nframes, int nsteps, sq_frame_rec *recs, double *xavg) {
+    if (!c || c->p.kernel != SQ_KERNEL_COMPAT1D || c->pending || !recs) return SQ_ERR_INVALID;
+    if (nframes < 0 || nframes > SQ_FRAMES_MAX || nsteps < 1) return SQ_ERR_INVALID;
+    int rc = sq_set_dev(c);
+    if (rc) return rc;
+    const int N = (int)c->p.dims[0];
+    for (int k = 0; k < nframes; ++k)
+        if ((rc = enqueue_compat(c, 1.0 /* unused: the controller block holds dtau */, nsteps, 0, true))) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->timing && (rc = sq_timing_collect(c, (size_t)-1))) return rc;
+    std::vector<Compat1DFrameRec> log((size_t)SQ_FRAMES_MAX);
+    CK(cudaMemcpy(log.data(), c->c_log_rec, sizeof(Compat1DFrameRec) * log.size(), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < nframes; ++k) {
+        const int slot = (int)((c->c_frames_done + k) % SQ_FRAMES_MAX);
+        recs[k].dtau = log[(size_t)slot].dtau;
+        recs[k].stable = log[(size_t)slot].stable;
+        recs[k].steps = log[(size_t)slot].steps;
+        if (xavg && log[(size_t)slot].stable)
+            CK(cudaMemcpy(xavg + (size_t)k * N, c->c_log_xavg + (size_t)slot * N, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
+    }
+    c->c_frames_done += nframes;
+    Compat1DCtl h{};
+    CK(cudaMemcpy(&h, c->c_ctl, sizeof h, cudaMemcpyDeviceToHost));
+    c->runs = h.runs;
+    if (nframes > 0) {
+        c->last_stable = recs[nframes - 1].stable;
+        c->last_steps = recs[nframes - 1].steps;
+    }
     return SQ_OK;
 }

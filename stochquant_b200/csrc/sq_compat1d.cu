@@ -84,8 +84,15 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
     __shared__ u64 sh_seed;        // full-u64 seed at the start of the current step
 
     const int pot = A.potential;
-    const double dt = A.dt, dtau = A.dtau;
     const int midpt = N / 2;
+    // controller mode: this frame's step size and counter come from the device block; the two noise
+    // scales are the host's expressions (sq_api.cu: enqueue_compat) evaluated here -- sqrtf is IEEE
+    // correctly rounded on both sides, the casts are the reference's (tau_kernel.cl:105,112)
+    const double dt = A.dt;
+    const double dtau = A.ctl ? A.ctl->dtau : A.dtau;
+    const long long runs0 = A.ctl ? A.ctl->runs : A.runs;
+    const double nscale_site = A.ctl ? dmul(A.noise_c, (double)sqrtf((float)ddiv_cold(dmul(2., dtau), dt))) : A.nscale_site;
+    const double nscale_omega = A.ctl ? dmul(A.noise_c, (double)sqrtf((float)dmul(2., dtau))) : A.nscale_omega;
 
     for (int i = tid; i < N; i += blockDim.x) {
         f_s[i] = A.f[i];
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
         const int E0 = sh_lrgEl;
         const double Vl0 = sh_lrgVl;
         const double stale = nfp_s[E0];
-        const double n_inv_den = (double)(A.runs + j + 1);  // (double)(*runs+j+1), :144
+        const double n_inv_den = (double)(runs0 + j + 1);  // (double)(*runs+j+1), :144
         const double r_n = __drcp_rn(n_inv_den);
         const double fmid = f_s[midpt];
         const double clmid = clas(dmul((double)midpt, dt), om, pot);
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
             if (i > N) continue;
             const double r = noise_accurate(t1_r[k], t2_r[k]);
             if (i == N) {  // the omega work-item, :103-110, :155-167
-                const double dw = dmul(A.nscale_omega, r);
+                const double dw = dmul(nscale_omega, r);
                 const double newomega = dadd(om, dmul(A.intconst, dw));
                 const double top = dmul((double)(N - 1), dt);
                 double o;
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
                 sh_om[cur ^ 1] = o;
                 continue;
             }
-            const double dw = dmul(A.nscale_site, r);
+            const double dw = dmul(nscale_site, r);
             const double fi = f_s[i];
             const double cl = clas(dmul((double)i, dt), om, pot);
             double inner;
@@ -336,6 +343,43 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
         *A.lrgVl = sh_lrgVl;
         *A.stable = unstable ? 0 : 1;
         *A.steps_done = j;
+    }
+    // ---- controller mode: log the frame, adapt the step size (tauhost.c:517-545) ---------------
+    if (A.ctl) {
+        const int fr = A.ctl->frame;  // (read by every thread before thread 0 updates it below)
+        const int slot = fr % A.log_cap;
+        if (!unstable) {
+            __syncthreads();  // x_r / xx0_r of the mid point were stored to A.x / A.xx0 above
+            const double xm = A.x[midpt];
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                const int i = tid * IPT + k;
+                if (i < N) A.log_xavg[(size_t)slot * N + i] = dsub(xx0_r[k], dmul(x_r[k], xm));
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            A.log_rec[slot].dtau = dtau;
+            A.log_rec[slot].stable = unstable ? 0 : 1;
+            A.log_rec[slot].steps = j;
+            double nd = dtau;
+            int sc = A.ctl->stab_cnt;
+            if (!unstable) {
+                if (sc > 10) {  // :523-528
+                    sc = 0;
+                    nd = ddiv_cold(dtau, 0.950);
+                }
+                ++sc;
+                A.ctl->runs = runs0 + A.loops;
+            } else {  // :533-545
+                nd = dmul(dtau, 0.950);
+                sc = 0;
+                *A.stable = 1;  // the host re-arms the flag (:542-544)
+            }
+            A.ctl->dtau = nd;
+            A.ctl->stab_cnt = sc;
+            A.ctl->frame = fr + 1;
+        }
     }
 }
 

@@ -48,6 +48,10 @@ struct sq_ctx {
            *c_newxx0 = nullptr, *c_omega = nullptr, *c_lrgVl = nullptr, *c_red = nullptr;
     u64 *c_seed = nullptr, *c_nevents = nullptr;
     int *c_stable = nullptr, *c_lrgEl = nullptr, *c_steps = nullptr;
+    sq::Compat1DCtl *c_ctl = nullptr;          // device-side frame controller (f-3)
+    sq::Compat1DFrameRec *c_log_rec = nullptr;
+    double *c_log_xavg = nullptr;
+    int64_t c_frames_done = 0;                 // frames run through the controller (log slot = frame % cap)
 
     // ---- lattice ----
     void *l_field[2] = {nullptr, nullptr};

@@ -17,6 +17,19 @@ __host__ __device__ inline u64 event_key(int step, int chain, u64 gid) {
 }
 
 // ---------------------------------------------------------------- compat 1-D ----
+// Device-side frame controller (the host logic of tauhost.c:504-545 moved next to
+// the kernel): when Compat1DArgs::ctl is set, the frame takes dtau / runs from this block, and its
+// epilogue applies the reference's accept / reject + step-size adaptation and logs what the host prints.
+struct Compat1DCtl {
+    double dtau;        // step size of the NEXT frame
+    long long runs;     // tau-steps accumulated into the running means (tauhost.c:554 `runs`)
+    int stab_cnt;       // consecutive stable frames (tauhost.c:523-528)
+    int frame;          // frames executed through the controller so far
+};
+struct Compat1DFrameRec {
+    double dtau;        // step size the frame ran with (the value its stdout line shows)
+    int stable, steps;  // frame accepted? ; tau-steps executed
+};
 struct Compat1DArgs {
     int N, loops, potential;
     long long runs;
@@ -33,6 +46,12 @@ struct Compat1DArgs {
     int *stable, *lrgEl, *steps_done;
     double *lrgVl;
     u64 *nevents;
+    // controller mode (null: the host passes dtau / runs and reads `stable` back every frame)
+    Compat1DCtl *ctl;
+    Compat1DFrameRec *log_rec;  // [log_cap]
+    double *log_xavg;           // [log_cap][N]  xx0[i] - x[i] x[mid] after an accepted frame (tauhost.c:519-521)
+    int log_cap;
+    double noise_c;             // `C`: the noise scales depend on dtau and are derived in the kernel
 };
 cudaError_t launch_compat1d(const Compat1DArgs &A, cudaStream_t stream);
 

@@ -51,6 +51,13 @@ class SqRngEntry(C.Structure):
                 ("ov_t1", C.c_uint64), ("ov_t2", C.c_uint64)]
 
 
+class SqFrameRec(C.Structure):
+    _fields_ = [("dtau", C.c_double), ("stable", C.c_int32), ("steps", C.c_int32)]
+
+
+SQ_FRAMES_MAX = 64
+
+
 def library_path() -> str:
     # SQ_LIBRARY: tuning builds of the same library (tools/); the product is libsq.so
     return os.environ.get("SQ_LIBRARY") or os.path.join(PKG, "libsq.so")
@@ -127,6 +134,12 @@ def load() -> C.CDLL:
     L.sq_kernel_time.argtypes = [vp, pd, C.POINTER(i64)]
     L.sq_lcg_jump.restype = u64
     L.sq_lcg_jump.argtypes = [u64, u64, u64]
+    L.sq_controller_set.restype = i32
+    L.sq_controller_set.argtypes = [vp, dbl, i64, i32]
+    L.sq_controller_get.restype = i32
+    L.sq_controller_get.argtypes = [vp, pd, C.POINTER(i64), C.POINTER(i32)]
+    L.sq_frames.restype = i32
+    L.sq_frames.argtypes = [vp, i32, i32, C.POINTER(SqFrameRec), pd]
     L.sq_session_open.restype = i32
     L.sq_session_open.argtypes = [C.POINTER(vp), C.c_char_p, i32, i32]
     L.sq_session_barrier.restype = i32
@@ -340,6 +353,24 @@ class Context:
                   "nclamped", "nevents", "steps_done"):
             out[k] = getattr(o, k)
         return out
+
+    # -- frame controller on the device (compat1d, sq.h: sq_controller_* / sq_frames)
+    def controller_set(self, dtau: float, runs: int = 0, stab_cnt: int = 0):
+        self._check(self.L.sq_controller_set(self._h, dtau, runs, stab_cnt), "sq_controller_set")
+
+    def controller_get(self):
+        d, r, s_ = C.c_double(), C.c_int64(), C.c_int32()
+        self._check(self.L.sq_controller_get(self._h, C.byref(d), C.byref(r), C.byref(s_)), "sq_controller_get")
+        return d.value, r.value, s_.value
+
+    def frames(self, nframes: int, nsteps: int):
+        """nframes frames back to back under the device-side controller -> (records, xavg[nframes][N])."""
+        recs = (SqFrameRec * max(1, nframes))()
+        xavg = np.full((max(1, nframes), self.vlocal), np.nan)
+        self._check(self.L.sq_frames(self._h, nframes, nsteps, recs, _dp(xavg)), "sq_frames")
+        out = [(recs[k].dtau, recs[k].stable, recs[k].steps) for k in range(nframes)]
+        self.runs = self.controller_get()[1]
+        return out, xavg[:nframes]
 
     def kernel_timing(self, enable: bool):
         self._check(self.L.sq_kernel_timing(self._h, int(enable)), "sq_kernel_timing")

@@ -132,3 +132,52 @@ def test_runs_offset_and_restart_state(gpu_sq, oracle):
     assert g.step(dtau, 30, runs0=5000) and o.frame(30)
     m = g.measure()
     assert maxabs(m["x"], o.x) < ATOL and maxabs(m["xx0"], o.xx0) < ATOL and m["runs"] == 5030
+
+
+# ---------------------------------------------------------------------------------------------
+# f-3: the frame controller on the device (sq_controller_* / sq_frames) against the same rules applied
+# by the host frame by frame (host/tauhost.c, tauhost.c:504-545): BIT-identical trajectories
+@pytest.mark.parametrize("pot,N,dt,dtau0", [(3, 200, .02, .002), (0, 100, .1, 3e-3)])
+def test_device_controller_equals_host_loop(gpu_sq, oracle, pot, N, dt, dtau0):
+    """The preset step size is above the Euler limit on purpose (taumain.py:102-104): the first frames
+    are rejected and dtau shrinks, later it grows again -- every branch of the controller runs."""
+    f, om, r1 = oracle.host_init(N, dt, dtau0)
+    loops, frames = 50, 90
+    a = gpu_sq.Context([N], kernel="compat1d", potential=pot, spacing=dt, f0=f, omega0=om, seed=r1)
+    b = gpu_sq.Context([N], kernel="compat1d", potential=pot, spacing=dt, f0=f, omega0=om, seed=r1)
+    # host loop
+    dtau, runs, stab = dtau0, 0, 0
+    host = []
+    for _ in range(frames):
+        st = a.step(dtau, loops, runs)
+        host.append((dtau, int(st), a.measure()["steps_done"]))
+        if st:
+            if stab > 10:
+                stab, dtau = 0, dtau / 0.950
+            stab += 1
+            runs += loops
+        else:
+            dtau, stab = dtau * 0.950, 0
+    # device controller, in batches that do not divide the frame count
+    b.controller_set(dtau0, 0, 0)
+    dev, xav = [], []
+    left = frames
+    while left:
+        n = min(left, 37)
+        r, x = b.frames(n, loops)
+        dev += r
+        xav += list(x)
+        left -= n
+    assert [h[1] for h in host] == [d[1] for d in dev], "accept / reject sequence"
+    assert [h[0] for h in host] == [d[0] for d in dev], "dtau sequence must be bit-identical"
+    assert [h[2] for h in host] == [d[2] for d in dev]
+    assert any(d[1] == 1 for d in dev) and (pot != 3 or any(d[1] == 0 for d in dev))
+    ma, mb = a.measure(), b.measure()
+    for k in ("f", "x", "xx0"):
+        assert np.array_equal(ma[k], mb[k]), k
+    assert ma["seed"] == mb["seed"] and ma["omega"] == mb["omega"] and ma["lrgEl"] == mb["lrgEl"]
+    assert b.controller_get() == (dtau, runs, stab)
+    # the logged xavg of the last accepted frame is the host's xx0 - x*x[mid]
+    last = max(k for k, d in enumerate(dev) if d[1] == 1)
+    if last == frames - 1:
+        assert np.array_equal(xav[last], ma["xx0"] - ma["x"] * ma["x"][N // 2])
