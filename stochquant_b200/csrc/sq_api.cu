@@ -1025,14 +1025,7 @@ extern "C" int sq_kernel_time(sq_ctx *c, double *ms_total, int64_t *launches) {
 }
 
 extern "C" uint64_t sq_lcg_jump(uint64_t seed, uint64_t gid0, uint64_t ndraws) {
-    static std::vector<JumpEntry> tab;
-    static bool built = false;
-    if (!built) {
-        tab.resize(JUMP_TABLE_ENTRIES);
-        build_jump_table(tab.data());
-        built = true;
-    }
-    return lcg_seed_at(seed, gid0, ndraws, tab.data());
+    return lcg_seed_at(seed, gid0, ndraws, host_jump_table());
 }
 
 extern "C" int sq_slab_stats(sq_ctx *c, uint64_t *finder_scans, uint64_t *agree_rounds) {

@@ -109,6 +109,16 @@ inline void build_jump_table(JumpEntry *tab /* JUMP_TABLE_ENTRIES */) {
     }
 }
 
+// process-wide host copy of the table (C++11 magic static: built once, thread-safe)
+inline const JumpEntry *host_jump_table() {
+    struct Holder {
+        JumpEntry t[JUMP_TABLE_ENTRIES];
+        Holder() { build_jump_table(t); }
+    };
+    static const Holder h;
+    return h.t;
+}
+
 // start seed S' at gid 0 whose event-free chain passes through seed `bs` before the draw at gid bg
 inline u64 virtual_start_seed(u64 bs, u64 bg, const JumpEntry *tab) {
     const u64 c0 = lcg_seed_at(0, 0, bg, tab);

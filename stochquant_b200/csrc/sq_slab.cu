@@ -156,13 +156,7 @@ __global__ void slab_flags_kernel(unsigned *f0, unsigned *f1, unsigned tag) {
 extern "C" int sq_rng_resolve(uint64_t step_seed, const sq_rng_entry *entries, int n, uint64_t gid, sq_rng_entry *out,
                               int *ndraws, int *plus) {
     if (!out || n < 0 || (n > 0 && !entries)) return SQ_ERR_INVALID;
-    static std::vector<JumpEntry> tab;
-    static bool built = false;
-    if (!built) {
-        tab.resize(JUMP_TABLE_ENTRIES);
-        build_jump_table(tab.data());
-        built = true;
-    }
+    const JumpEntry *tab = host_jump_table();
     u64 bg = 0, bs = step_seed;
     for (int k = 0; k < n; ++k)
         if (entries[k].gid_start <= gid && entries[k].gid_start >= bg) {
@@ -171,7 +165,7 @@ extern "C" int sq_rng_resolve(uint64_t step_seed, const sq_rng_entry *entries, i
         }
     u64 sfull = bs;
     if (gid != bg) {  // the draw at gid-1 was event-free: seed = t2(gid-1) - 2^31 as a wrapping u64
-        const u64 sp = (gid - 1 == bg) ? bs : lcg_seed_at(bs, bg, gid - 1 - bg, tab.data());
+        const u64 sp = (gid - 1 == bg) ? bs : lcg_seed_at(bs, bg, gid - 1 - bg, tab);
         u64 t1, t2;
         lcg_draw(sp, gid - 1, t1, t2);
         sfull = lcg_next_seed(t2);
