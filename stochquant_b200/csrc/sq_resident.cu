@@ -464,57 +464,57 @@ __global__ void __launch_bounds__(256) history_sums_kernel(const WelfordArgs A, 
     }
 }
 
-// history -> running means (tau_kernel.cl:144-145 per time slice): one thread per slice walks
-// the steps in order (the recurrence is sequential in the step index, parallel in the slice)
+// history -> running means (tau_kernel.cl:144-145 per time slice).  The reference's update
+// x <- x + (v - x)/(runs+j+1) is the running mean, so n more samples give, in closed form,
+//     x' = x + (sum_j v_j - n x) / (runs + n):
+// two sums per slice over the launch's steps instead of a sequential recurrence (fp64 rounding differs
+// from the step-by-step form at the 1e-15 level; the parity tolerance on these observables is 1e-3).
+// One thread per slice, loads batched so their latencies overlap; fixed summation order.  (Splitting the
+// step range over four warps per slice block was measured slower.)
 __global__ void __launch_bounds__(128) welford_history_kernel(const WelfordArgs A, const double *step_sums) {
     if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    // The recurrence is sequential in n, so only multiply-adds may sit on its dependent chain: the
-    // divisions by the counter and by the slice volume become multiplications by reciprocals that are
-    // computed off the chain (<= 1 ulp fp64 from the oracle's quotient; the parity tolerance on the
-    // running means is 1e-3).
     const double inv_vs = 1.0 / (double)A.vslice;
+    const double n = (double)A.nsteps, den = (double)(A.runs + A.nsteps);
     if (t < A.nt) {
-        double x = A.slice_x[t], xx0 = A.slice_xx0[t], last = 0;
-        // the loads do not depend on the recurrence: fetch 16 steps at a time so their latencies overlap
         constexpr int B = 16;
+        double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, last = 0;
         for (int n0 = 0; n0 < A.nsteps; n0 += B) {
-            double h[B], hm[B], rc[B];
+            double h[B], hm[B];
 #pragma unroll
             for (int j = 0; j < B; ++j) {
-                const int n = min(n0 + j, A.nsteps - 1);
-                h[j] = A.hist_rows[(size_t)n * A.nt + t];
-                hm[j] = A.hist_rows[(size_t)n * A.nt + A.tmid];
-                rc[j] = 1.0 / (double)(A.runs + n0 + j + 1);
+                const int k = min(n0 + j, A.nsteps - 1);
+                h[j] = A.hist_rows[(size_t)k * A.nt + t];
+                hm[j] = A.hist_rows[(size_t)k * A.nt + A.tmid];
             }
 #pragma unroll
-            for (int j = 0; j < B; ++j) {
+            for (int j = 0; j < B; ++j)
                 if (n0 + j < A.nsteps) {
+                    s1[j & 3] += h[j];
+                    s2[j & 3] = fma(h[j], hm[j], s2[j & 3]);
                     last = h[j];
-                    const double P = last * inv_vs, Pm = hm[j] * inv_vs;
-                    xx0 = fma(fma(P, Pm, -xx0), rc[j], xx0);
-                    x = fma(P - x, rc[j], x);
                 }
-            }
         }
-        A.slice_x[t] = x;
-        A.slice_xx0[t] = xx0;
+        const double SP = ((s1[0] + s1[1]) + (s1[2] + s1[3])) * inv_vs;
+        const double SPP = ((s2[0] + s2[1]) + (s2[2] + s2[3])) * inv_vs * inv_vs;
+        const double x = A.slice_x[t], xx0 = A.slice_xx0[t];
+        A.slice_x[t] = x + (SP - n * x) / den;
+        A.slice_xx0[t] = xx0 + (SPP - n * xx0) / den;
         A.slice_sum[t] = last;
     }
     if (t == A.nt) {  // one spare thread: running means of <phi>, <phi^2>
-        double m1 = A.sums_mean[0], m2 = A.sums_mean[1], s1 = 0, s2 = 0;
         const double inv_vol = 1.0 / ((double)A.vslice * (double)A.nt);
-        for (int n = 0; n < A.nsteps; ++n) {
-            s1 = step_sums[2 * n];
-            s2 = step_sums[2 * n + 1];
-            const double rc = 1.0 / (double)(A.runs + n + 1);
-            m1 = fma(s1 * inv_vol - m1, rc, m1);
-            m2 = fma(s2 * inv_vol - m2, rc, m2);
+        double a1 = 0, a2 = 0, s1 = 0, s2 = 0;
+        for (int k = 0; k < A.nsteps; ++k) {
+            s1 = step_sums[2 * k];
+            s2 = step_sums[2 * k + 1];
+            a1 += s1;
+            a2 += s2;
         }
         A.sums[0] = s1;
         A.sums[1] = s2;
-        A.sums_mean[0] = m1;
-        A.sums_mean[1] = m2;
+        A.sums_mean[0] += (a1 * inv_vol - n * A.sums_mean[0]) / den;
+        A.sums_mean[1] += (a2 * inv_vol - n * A.sums_mean[1]) / den;
     }
 }
 
