@@ -86,7 +86,7 @@ __device__ __noinline__ void finder_cold(u64 *found, u64 sm, u64 g0, int w) {
 // chain from seed bs".  No memory traffic.  Both events are decidable from the SEED sequence z
 // (z' = ALPHA z + BETA g + GAMMA: one 48-bit multiply-add per site instead of the two of a draw):
 //   inf-retry  t1 < 2^16        => (t1 mod 2^32) < 2^16, and the low 32 bits of t1 = z A + c are one IMAD;
-//   `seed+=`   z < 2^31 && ...  => (z >> 16) < 2^15.
+//   `seed+=`   z < 2^31 && ...  => bits 32..47 of z are zero.
 // One 3-input min per site collects both filters (threshold 2^16); candidates (p ~ 2^-15 per site)
 // are decided exactly on a cold path.  The strip-to-strip advance of a thread is one affine map with
 // a fixed stride in 32-bit limbs, as in sq_march.cu.
@@ -115,7 +115,9 @@ __global__ void __launch_bounds__(256) find_events_kernel(u64 bs, u64 bg, u64 g_
 #pragma unroll
         for (int e = 0; e < FW; ++e) {
             const unsigned t1l = z.lo * A_LO + ce;                  // t1 mod 2^32
-            const unsigned zs = __funnelshift_r(z.lo, z.hi, 16);    // z >> 16 (bits 16..47)
+            // z < 2^31 => bits 32..47 of z are zero => (z.hi << 16) == 0; a plain shift (the assembler
+            // may put it on the FMA pipe as IMAD.SHL: this kernel is ALU-pipe bound) instead of a funnel shift
+            const unsigned zs = z.hi << 16;
             m = min(min(m, t1l), zs);
             u64 p;
             unsigned pl, ph, t;
