@@ -6,6 +6,7 @@
 #include <fcntl.h>
 #include <sched.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -33,6 +34,10 @@ extern "C" int sq_session_open(sq_session **out, const char *name, int rank, int
     snprintf(s->name, sizeof s->name, "/sq_%s", name);
     s->rank = rank;
     s->nranks = nranks;
+    if (const char *t = getenv("SQ_SESSION_TIMEOUT")) {  // seconds a barrier waits for the other ranks
+        const double v = atof(t);
+        if (v > 0) s->timeout_s = v;
+    }
     // every rank may be the creator: a fresh segment is zero-filled, which is the initial state
     s->fd = shm_open(s->name, O_CREAT | O_RDWR, 0600);
     if (s->fd < 0 || ftruncate(s->fd, (off_t)sizeof(SessionShm)) != 0) {

@@ -128,3 +128,16 @@ def test_session_rejects_bad_arguments(sq):
     assert np.array_equal(s.allgather_u64([7, 8]), np.array([[7, 8]], dtype=np.uint64))
     s.barrier()
     s.close()
+
+
+def test_session_missing_rank_times_out(sq, tmp_path):
+    """A ring whose partner never shows up must fail (SQ_ERR_TIMEOUT), not hang."""
+    import subprocess, sys, time
+    code = ("import sys; sys.path.insert(0, %r); import stochquant_b200 as sq\n"
+            "try:\n    sq.Session('lonely' + %r, 0, 2)\n    print('opened')\n"
+            "except sq.SqError as e:\n    print('error', e.code)\n") % (ROOT, uuid.uuid4().hex[:8])
+    t0 = time.time()
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=60,
+                       env=dict(os.environ, SQ_SESSION_TIMEOUT="1.5"))
+    assert r.stdout.strip() == "error -6", (r.stdout, r.stderr)
+    assert time.time() - t0 < 30
