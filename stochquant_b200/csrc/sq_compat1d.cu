@@ -82,6 +82,10 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
     __shared__ double sh_lrgVl;
     __shared__ int sh_lrgEl, sh_unstable;
     __shared__ u64 sh_seed;        // full-u64 seed at the start of the current step
+    // block-parallel stability scan (IPT == 1): warp totals of the three prefix maxima, warp results
+    __shared__ double sc_tot[3][32];
+    __shared__ int sc_res[2][32];
+    __shared__ double sh_R0;
 
     const int pot = A.potential;
     const int midpt = N / 2;
@@ -134,19 +138,26 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
     int cur = 0;  // sh_om index holding the current omega
     int j = 0;
     int unstable = 0;
+    // IPT == 1: every thread derives the scan's results itself and carries them in registers
+    int E0c = sh_lrgEl;
+    double Vlc = sh_lrgVl;
     for (; j < A.loops; ++j) {
         const double om = sh_om[cur];
-        const int E0 = sh_lrgEl;
-        const double Vl0 = sh_lrgVl;
+        const int E0 = (IPT == 1) ? E0c : sh_lrgEl;
+        const double Vl0 = (IPT == 1) ? Vlc : sh_lrgVl;
         const double stale = nfp_s[E0];
         const double n_inv_den = (double)(runs0 + j + 1);  // (double)(*runs+j+1), :144
         const double r_n = __drcp_rn(n_inv_den);
         const double fmid = f_s[midpt];
         const double clmid = clas(dmul((double)midpt, dt), om, pot);
+        // the scan's reference value newf[lrgEl]+cl (:135) is known now: one thread prepares it while
+        // the others draw (visible after the barrier of phase 1)
+        if (IPT == 1 && tid == (int)blockDim.x - 1) sh_R0 = dadd(stale, clas(dmul((double)E0, dt), om, pot));
 
         // ---- phase 1: draws (speculative affine chain) -------------------------------
         u64 t1_r[IPT], t2_r[IPT];
         int ev = 0;
+        double my_v = -INFINITY, my_a = -INFINITY, my_d = 0.;  // IPT == 1: this thread's site for the scan
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
             const int i = tid * IPT + k;
@@ -237,14 +248,51 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
             v_s[i] = v;
             a_s[i] = absol(v);
             d_s[i] = absol(dsub(dsub(nf, fi), dw));
+            if (IPT == 1) {
+                my_v = v;
+                my_a = absol(v);
+                my_d = absol(dsub(dsub(nf, fi), dw));
+            }
             // :144-145, pre-update field
             const double path = dadd(fi, cl);
             xx0_r[k] = dadd(xx0_r[k], ddiv_by(dsub(dmul(path, dadd(fmid, clmid)), xx0_r[k]), n_inv_den, r_n));
             x_r[k] = dadd(x_r[k], ddiv_by(dsub(path, x_r[k]), n_inv_den, r_n));
         }
-        __syncthreads();
+        // ---- phase 3: field hand-over (all) + stability scan, :135-143 ---------------------
+        // IPT == 1 (N <= 1023, the reference's default 200): every thread holds its site's (v, a, d) in
+        // registers and the as-if-sequential scan is a block-wide exclusive prefix maximum:
+        //   record_i  <=>  v_i > T_i,   T_i = max(R0, max_{j<i} v_j)              if a record precedes lrgEl (case A)
+        //                              T_i = R0 (i < lrgEl) | max_{lrgEl<=j<i} v_j (i > lrgEl); i == lrgEl never records
+        //   unstable  <=>  some record has d_i > max(lrgVl, max_{j<i} a_j)
+        // (the per-site rule of the chunked scan below, which stays for IPT > 1).  The warp-level part
+        // runs BEFORE the barrier that ends phase 2, so no warp waits for another one's serial loop.
+        int caseA_blk = 0;
+        double pv = my_v, pu = -INFINITY, pa = my_a;
+        if (IPT == 1) {
+            const int lane = tid & 31, w = tid >> 5;
+            pu = (tid >= E0) ? my_v : -INFINITY;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double tv = __shfl_up_sync(0xffffffffu, pv, o);
+                const double tu = __shfl_up_sync(0xffffffffu, pu, o);
+                const double ta = __shfl_up_sync(0xffffffffu, pa, o);
+                if (lane >= o) {
+                    pv = fmax(pv, tv);
+                    pu = fmax(pu, tu);
+                    pa = fmax(pa, ta);
+                }
+            }
+            if (lane == 31) {
+                sc_tot[0][w] = pv;
+                sc_tot[1][w] = pu;
+                sc_tot[2][w] = pa;
+            }
+            // (sh_R0 was published by the barrier of phase 1)
+            caseA_blk = __syncthreads_or((tid < N && tid < E0 && my_v > sh_R0) ? 1 : 0);  // also ends phase 2
+        } else {
+            __syncthreads();
+        }
 
-        // ---- phase 3: field hand-over (all) + stability scan (warp 0), :135-143 -------
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
             const int i = tid * IPT + k;
@@ -253,7 +301,49 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
                 nfp_s[i] = nf_r[k];
             }
         }
-        if (tid < 32) {
+        if (IPT == 1) {
+            const int lane = tid & 31, w = tid >> 5, nw = (int)blockDim.x >> 5;
+            const double NEG = -INFINITY, R0 = sh_R0;
+            double ov = NEG, ou = NEG, oa = NEG, alla = NEG;  // maxima over the warps before this one / all
+            for (int q = 0; q < nw; ++q) {
+                const double tv = sc_tot[0][q], tu = sc_tot[1][q], ta = sc_tot[2][q];
+                if (q < w) {
+                    ov = fmax(ov, tv);
+                    ou = fmax(ou, tu);
+                    oa = fmax(oa, ta);
+                }
+                alla = fmax(alla, ta);
+            }
+            double ev_ = __shfl_up_sync(0xffffffffu, pv, 1), eu_ = __shfl_up_sync(0xffffffffu, pu, 1),
+                   ea_ = __shfl_up_sync(0xffffffffu, pa, 1);
+            if (lane == 0) ev_ = eu_ = ea_ = NEG;
+            ev_ = fmax(ev_, ov);
+            eu_ = fmax(eu_, ou);
+            ea_ = fmax(ea_, oa);
+            const double T = caseA_blk ? fmax(R0, ev_) : ((tid > E0) ? eu_ : R0);
+            const bool rec = (tid < N) && (caseA_blk || tid != E0) && (my_v > T);
+            const int unst_i = (rec && my_d > fmax(Vl0, ea_)) ? 1 : 0;
+            const int lr = __reduce_max_sync(0xffffffffu, rec ? tid : -1);
+            const unsigned ub = __ballot_sync(0xffffffffu, unst_i);
+            if (lane == 0) {
+                sc_res[0][w] = lr;
+                sc_res[1][w] = ub != 0u;
+            }
+            __syncthreads();
+            int lastrec = -1, unst = 0;
+            for (int q = 0; q < nw; ++q) {
+                lastrec = max(lastrec, sc_res[0][q]);
+                unst |= sc_res[1][q];
+            }
+            if (lastrec >= 0) E0c = lastrec;
+            Vlc = fmax(Vl0, alla);
+            unstable = unst;
+            if (tid == 0) {  // for the epilogue
+                sh_lrgEl = E0c;
+                sh_lrgVl = Vlc;
+                if (unst) sh_unstable = 1;
+            }
+        } else if (tid < 32) {
             const int lane = tid;
             const int chunk = (N + 31) / 32;
             const int b = lane * chunk, e = min(N, b + chunk);
@@ -312,9 +402,11 @@ __global__ void __launch_bounds__(1024, 1) compat1d_frame_kernel(Compat1DArgs A)
                 if (unst) sh_unstable = 1;
             }
         }
-        __syncthreads();
+        if (IPT != 1) {
+            __syncthreads();
+            unstable = sh_unstable;
+        }
         cur ^= 1;
-        unstable = sh_unstable;
         if (unstable) {  // :169-171
             ++j;
             break;
