@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(256, (REBASE || NDIM == 4 || sizeof(real) == 8
 
         // ---- per-site: draw, update ------------------------------------------------------
         Pack<real> res;
+        unsigned nclamp_strip = 0;
         Seed32 s32 = seed_split(s);
         u64 cg = site_const(g0);
         bool maybe = false;
@@ -200,13 +201,15 @@ __global__ void __launch_bounds__(256, (REBASE || NDIM == 4 || sizeof(real) == 8
             else v = O::fma(-c_2dt, phi, v);  // (-c_dt)(2 phi) == (-2 c_dt) phi exactly
             v = O::add(v, dw);
             const real vc = (v < (real)1000) ? ((v > -(real)1000) ? v : -(real)1000) : (real)1000;  // NaN -> +1000
-            nclamp += (vc != v) ? 1u : 0u;
+            nclamp_strip += (vc != v) ? 1u : 0u;
             res.v[e] = vc;
             acc1 = O::add(acc1, phi);
             acc2 = O::fma(phi, phi, acc2);
         }
+        bool replayed = false;  // an event in this strip: the launch is redone, its clamp hits are not counted
         if (!(REBASE && slow) && __builtin_expect(maybe, 0))
-            strip_events_cold(A.event_key, A.step_index, chain, s, g0, VEC);
+            replayed = strip_events_cold(A.event_key, A.step_index, chain, s, g0, VEC);
+        if (!replayed) nclamp += nclamp_strip;
         *reinterpret_cast<Pack<real> *>(dst + off) = res;
         // boundary slices also go straight into the neighbours' ghost buffers (posted NVLink writes)
         if (push_lo) *reinterpret_cast<Pack<real> *>(push_lo + off) = res;

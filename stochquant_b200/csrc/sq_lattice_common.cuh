@@ -45,13 +45,20 @@ __device__ __forceinline__ void rebase_lookup(const LatticeArgs &A, int chain, u
 }
 
 // cold paths, arguments by value (taking the address of a register array would spill it)
-__device__ __noinline__ void strip_events_cold(u64 *event_key_ptr, int step, int chain, u64 sm, u64 g0, int w) {
+// returns true if the strip holds an event: the launch will be replayed, so nothing this strip computed
+// (in particular a clamp hit caused by the +-inf of the draw that is about to be retried) may be counted
+__device__ __noinline__ bool strip_events_cold(u64 *event_key_ptr, int step, int chain, u64 sm, u64 g0, int w) {
+    bool any = false;
     for (int e = 0; e < w; ++e) {
         u64 t1, t2;
         lcg_draw(sm, g0 + e, t1, t2);
-        if (lcg_event(sm, t1, t2)) atomicMin((unsigned long long *)event_key_ptr, event_key(step, chain, g0 + e));
+        if (lcg_event(sm, t1, t2)) {
+            atomicMin((unsigned long long *)event_key_ptr, event_key(step, chain, g0 + e));
+            any = true;
+        }
         sm = lcg_next_seed(t2) & LCG_MASK;
     }
+    return any;
 }
 
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {

@@ -387,11 +387,12 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : MARCH_MINB) lattice_march_ke
         // ---- rare paths: possible RNG event in this strip, values at or beyond the clamp ---------
         const float amax = fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fabsf(v[2])), fabsf(v[3]));
         if (__builtin_expect((umin < 32768u) | !(amax < 1000.0f), 0)) {
-            if (umin < 32768u) strip_events_cold(A.event_key, A.step_index, chain, seed_join(s_strip), g0, 4);
+            bool replayed = false;
+            if (umin < 32768u) replayed = strip_events_cold(A.event_key, A.step_index, chain, seed_join(s_strip), g0, 4);
             const Clamped cl = clamp_cold(v[0], v[1], v[2], v[3]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) v[e] = cl.v[e];
-            nclamp += cl.n;
+            if (!replayed) nclamp += cl.n;
         }
 
         // ---- observables of the pre-update field, store ------------------------------------------

@@ -154,3 +154,20 @@ def test_c4_slab_size_ring_equals_single_context(gpu_sq):
     res = ring_threads(gpu_sq, 1, dims, None, [6], real="f32", math="fast")
     assert res[0]["seed"] == seed
     assert np.array_equal(res[0]["field"], ref)
+
+
+@pytest.mark.parametrize("gid", [0, 3, 4, 2047, 2048, 8191, 8192, 16383, 16384])
+def test_ring_events_on_marching_kernel(gpu_sq, oracle, gid):
+    """Forced events on a marching-kernel shape in a ring of two (slab boundary at gid 8192): found by the
+    finder, agreed through the session, applied through virtual start seeds on both ranks."""
+    dims = (32, 8, 8, 8)
+    V = int(np.prod(dims))
+    seed = seed_with_retry_at(oracle, gid)
+    rng = np.random.default_rng(22)
+    phi0 = rng.normal(size=V) * 0.5
+    o = oracle.LatticeOracle(dims, real=oracle.F32, potential=0, seed=seed, phi0=phi0)
+    res = ring_threads(gpu_sq, 2, dims, phi0, [4], real="f32", math="fast", seed=seed)
+    o.step(DTAU, 4)
+    assert o.L.nevents >= 1
+    check_against_oracle(res, o, dims, ATOL[("f32", "fast")], 50 * ATOL[("f32", "fast")])
+    assert all(r["nevents"] >= 1 for r in res)
