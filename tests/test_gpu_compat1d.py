@@ -181,3 +181,17 @@ def test_device_controller_equals_host_loop(gpu_sq, oracle, pot, N, dt, dtau0):
     last = max(k for k, d in enumerate(dev) if d[1] == 1)
     if last == frames - 1:
         assert np.array_equal(xav[last], ma["xx0"] - ma["x"] * ma["x"][N // 2])
+
+
+def test_frames_argument_checks(gpu_sq, oracle):
+    f, om, r1 = oracle.host_init(50, .05, 1e-3)
+    g = gpu_sq.Context([50], kernel="compat1d", potential=0, spacing=.05, f0=f, omega0=om, seed=r1)
+    g.controller_set(1e-3, 0, 0)
+    recs, _ = g.frames(0, 10)
+    assert recs == []
+    with pytest.raises(gpu_sq.SqError):
+        g.frames(gpu_sq.SQ_FRAMES_MAX + 1, 10)
+    with pytest.raises(gpu_sq.SqError):
+        g.controller_set(0.0, 0, 0)
+    recs, xav = g.frames(gpu_sq.SQ_FRAMES_MAX, 5)  # a full log
+    assert len(recs) == gpu_sq.SQ_FRAMES_MAX and g.controller_get()[1] == 5 * sum(r[1] for r in recs)

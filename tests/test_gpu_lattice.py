@@ -351,3 +351,70 @@ def test_march_kernel_is_the_one_tested(gpu_sq):
     b.step(DTAU, 7)
     assert a.measure()["seed"] == b.measure()["seed"]
     assert np.array_equal(a.download(), b.download())  # ACCURATE: identical operation sequence in both kernels
+
+
+def _seed_with_event_in_step(oracle, V, gid, step):
+    """Step-start seed S_0 such that the chain meets an inf-retry at `gid` in tau-step `step` (0-based):
+    the seed of that step is constructed directly, then `step` whole event-free steps are inverted."""
+    M = 2**48
+    target = seed_with_retry_at(oracle, gid)
+
+    def step_fwd(S):
+        s = oracle.lib().sqo_jump(S, 0, V)
+        _, rec = oracle.random(s, V)
+        return rec.seed_after & (M - 1)
+    c = step_fwd(0)
+    P = (step_fwd(1) - c) % M
+    Pinv = pow(P, -1, M)
+    S = target
+    for _ in range(step):
+        S = ((S - c) * Pinv) % M
+    return S
+
+
+def test_resident_event_after_a_checkpoint(gpu_sq, oracle):
+    """Event in step 300 of a 450-step resident launch: the launch leaves early, the host resumes from the
+    checkpoint of step 256 (every 128 steps), reruns 44 steps, takes the event in a streaming step and
+    finishes on chip.  Seeds bit-exact, running means over all 450 steps."""
+    dims = (128, 40)
+    V = 128 * 40
+    S = _seed_with_event_in_step(oracle, V, 3001, 300)
+    g, o = pair(gpu_sq, oracle, dims, "f32", "fast", seed=S)
+    g.step(DTAU, 450)
+    o.step(DTAU, 450)
+    m = g.measure()
+    assert o.L.nevents >= 1 and m["nevents"] >= 1
+    assert m["seed"] == o.seed and m["runs"] == 450
+    assert maxabs(g.download(), o.field) < ATOL[("f32", "fast")]
+    assert maxabs(m["slice_x"], o.slice_x) < 1e-4 and maxabs(m["slice_xx0"], o.slice_xx0) < 1e-4
+    assert m["nclamped"] == 0
+
+
+def test_march_kernel_3d_event(gpu_sq, oracle):
+    dims = (64, 16, 16)  # 16 threads per row, one row per thread: the 3-D instance of the marching kernel
+    V = int(np.prod(dims))
+    seed = seed_with_retry_at(oracle, 5003)
+    g, o = pair(gpu_sq, oracle, dims, "f32", "fast", 0, seed=seed)
+    g.step(DTAU, 4)
+    o.step(DTAU, 4)
+    m = g.measure()
+    assert o.L.nevents >= 1 and m["nevents"] >= 1 and m["seed"] == o.seed
+    assert maxabs(g.download(), o.field) < ATOL[("f32", "fast")]
+    assert m["nclamped"] == 0
+
+
+def test_event_in_one_chain_of_a_batch(gpu_sq, oracle):
+    """Batched chains on the marching kernel: a replay entry belongs to ONE chain; the others must not see it."""
+    dims, nch = (32, 8, 8, 8), 3
+    seeds = [1242608872, seed_with_retry_at(oracle, 4099), 1242608873]
+    g = gpu_sq.Context(dims, real="f32", math="fast", potential=4, nchains=nch)
+    for k in range(nch):
+        g.set_chain(k, seeds[k], 0.25, 0.5)
+    g.step(DTAU, 3)
+    _, _, got = g.measure_chains()
+    for k in range(nch):
+        o = oracle.LatticeOracle(dims, real=oracle.F32, potential=4, m2=0.25, lam=0.5, seed=seeds[k])
+        o.step(DTAU, 3)
+        assert int(got[k]) == o.seed, k
+        assert maxabs(g.download(chain=k), o.field) < ATOL[("f32", "fast")], k
+    assert g.measure()["nevents"] >= 1
