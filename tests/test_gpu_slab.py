@@ -171,3 +171,16 @@ def test_ring_events_on_marching_kernel(gpu_sq, oracle, gid):
     assert o.L.nevents >= 1
     check_against_oracle(res, o, dims, ATOL[("f32", "fast")], 50 * ATOL[("f32", "fast")])
     assert all(r["nevents"] >= 1 for r in res)
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_ring_thin_slabs(gpu_sq, oracle, nranks):
+    """Four time slices over 2 or 4 ranks: with one slice per rank the same slice is the lower AND the upper
+    boundary (it waits on both neighbours and pushes to both); with two there is no interior at all."""
+    dims = (32, 8, 8, 4)
+    rng = np.random.default_rng(23)
+    phi0 = rng.normal(size=int(np.prod(dims))) * 0.5
+    o = oracle.LatticeOracle(dims, real=oracle.F32, potential=4, m2=0.25, lam=0.5, phi0=phi0)
+    res = ring_threads(gpu_sq, nranks, dims, phi0, [3, 8], real="f32", math="fast", pot=4, m2=0.25, lam=0.5)
+    o.step(DTAU, 11)
+    check_against_oracle(res, o, dims, ATOL[("f32", "fast")], 50 * ATOL[("f32", "fast")])
