@@ -418,3 +418,25 @@ def test_event_in_one_chain_of_a_batch(gpu_sq, oracle):
         assert int(got[k]) == o.seed, k
         assert maxabs(g.download(chain=k), o.field) < ATOL[("f32", "fast")], k
     assert g.measure()["nevents"] >= 1
+
+
+def test_free_field_ensemble_4d_marching_kernel(gpu_sq):
+    """Observables within statistical error on the marching kernel: <phi^2> of the 4-D free field (potID 0:
+    F = 2 phi) against the analytic stationary value of the Euler-discretised Langevin process,
+    <phi^2> = mean_k 1 / (lam_k (1 - eps lam_k / 2)),  lam_k = sum_mu 4 sin^2(k_mu/2) + 2."""
+    L = 16
+    eps = 0.05  # stability limit 2 / (16 + 2)
+    g = gpu_sq.Context((L, L, L, L), real="f32", math="fast", potential=0)
+    g.step(eps, 400)
+    vals = []
+    for _ in range(240):
+        g.step(eps, 5)
+        vals.append(g.measure()["mean_phi2"])
+    k = 2 * np.pi * np.arange(L) / L
+    s2 = 4 * np.sin(k / 2) ** 2
+    lam = s2[:, None, None, None] + s2[None, :, None, None] + s2[None, None, :, None] + s2[None, None, None, :] + 2.0
+    want = float(np.mean(1.0 / (lam * (1 - eps * lam / 2))))
+    vals = np.array(vals)
+    bins = vals.reshape(20, -1).mean(axis=1)  # binned error (autocorrelation)
+    err = bins.std(ddof=1) / np.sqrt(len(bins))
+    assert abs(vals.mean() - want) < 5 * err + 1e-3 * want, (vals.mean(), want, err)
