@@ -112,6 +112,7 @@ extern "C" void sq_free(sq_ctx *c) {
     }
     if (c->fin_stream) { cudaStreamSynchronize(c->fin_stream); cudaStreamDestroy(c->fin_stream); }
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->h_pin2) cudaFreeHost(c->h_pin2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -843,15 +844,27 @@ extern "C" int sq_measure(sq_ctx *c, sq_obs *o) {
     const int nt = c->nt;
     CK(launch_reduce_field(c->l_field[c->cur], p.real, c->vlocal, p.nchains, c->l_redbuf, c->stream));
     c->launches++;
-    std::vector<double> part((size_t)REDUCE_BLOCKS * 2), sx((size_t)nt), sxx((size_t)nt);
-    CK(cudaMemcpyAsync(part.data(), c->l_redbuf, sizeof(double) * part.size(), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(sx.data(), c->l_slice_x, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(sxx.data(), c->l_slice_xx0, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
-    unsigned long long ncl = 0;
-    u64 seed0 = 0;
-    CK(cudaMemcpyAsync(&ncl, c->l_nclamped, sizeof ncl, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(&seed0, c->l_seeds[c->cur], sizeof seed0, cudaMemcpyDeviceToHost, c->stream));
+    // all read-backs go through one pinned scratch buffer: truly asynchronous copies, one synchronisation
+    // (pageable destinations would make each of the five copies a blocking staged transfer)
+    const size_t need = sizeof(double) * ((size_t)REDUCE_BLOCKS * 2 + 2 * (size_t)nt + 2);
+    if (need > c->h_pin2_bytes) {
+        if (c->h_pin2) CK(cudaFreeHost(c->h_pin2));
+        c->h_pin2 = nullptr;
+        c->h_pin2_bytes = 0;
+        CK(cudaMallocHost(&c->h_pin2, need));
+        c->h_pin2_bytes = need;
+    }
+    double *part = (double *)c->h_pin2, *sxp = part + (size_t)REDUCE_BLOCKS * 2, *sxxp = sxp + nt;
+    unsigned long long *tail = (unsigned long long *)(sxxp + nt);  // [0] = nclamped, [1] = seed
+    CK(cudaMemcpyAsync(part, c->l_redbuf, sizeof(double) * (size_t)REDUCE_BLOCKS * 2, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sxp, c->l_slice_x, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sxxp, c->l_slice_xx0, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(tail, c->l_nclamped, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(tail + 1, c->l_seeds[c->cur], sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    const unsigned long long ncl = tail[0];
+    const u64 seed0 = tail[1];
+    const std::vector<double> sx(sxp, sxp + nt), sxx(sxxp, sxxp + nt);
     double s1 = 0, s2 = 0;
     for (int k = 0; k < REDUCE_BLOCKS; ++k) { s1 += part[2 * k]; s2 += part[2 * k + 1]; }
     o->mean_phi = s1 / (double)c->vlocal;

@@ -42,6 +42,8 @@ struct sq_ctx {
     int64_t last_steps = 0;
     uint64_t nevents = 0;
     void *h_pin = nullptr;  // pinned scratch (4 KB)
+    void *h_pin2 = nullptr; // pinned scratch of sq_measure (lattice), grown on demand
+    size_t h_pin2_bytes = 0;
 
     // ---- compat 1-D ----
     double *c_f = nullptr, *c_x = nullptr, *c_xx0 = nullptr, *c_newf = nullptr, *c_newx = nullptr,
