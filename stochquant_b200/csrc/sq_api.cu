@@ -663,9 +663,14 @@ static int sync_lattice(sq_ctx *c) {
     int done = 0;
     int64_t runs0 = c->pend_runs0;
     while (total > 0) {
+        // the event word (and the resident kernel's error flag) ride behind the kernels into pinned
+        // memory: one synchronisation, no blocking pageable copies on the per-frame path
+        u64 *pin_key = (u64 *)c->h_pin;
+        unsigned *pin_err = (unsigned *)((char *)c->h_pin + 64);
+        CK(cudaMemcpyAsync(pin_key, c->l_event, sizeof(u64), cudaMemcpyDeviceToHost, c->stream));
+        if (c->pend_kind == 1) CK(cudaMemcpyAsync(pin_err, c->r_error, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        u64 key;
-        CK(cudaMemcpy(&key, c->l_event, sizeof(u64), cudaMemcpyDeviceToHost));
+        u64 key = *pin_key;
         const int n = c->pend_nsteps;
         if (c->timing) {
             size_t valid = (size_t)-1;  // streaming: launches up to and including the event step ran in full
@@ -674,8 +679,7 @@ static int sync_lattice(sq_ctx *c) {
             if (rt) return rt;
         }
         if (c->pend_kind == 1) {
-            unsigned err = 0;
-            CK(cudaMemcpy(&err, c->r_error, sizeof err, cudaMemcpyDeviceToHost));
+            const unsigned err = *pin_err;
             if (err) return SQ_ERR_TIMEOUT;
             if (key == NO_EVENT) {
                 c->cur ^= 1;  // one launch, one buffer flip
