@@ -1088,13 +1088,18 @@ extern "C" int sq_frames(sq_ctx *c, int nframes, int nsteps, sq_frame_rec *recs,
     if (c->timing && (rc = sq_timing_collect(c, (size_t)-1))) return rc;
     std::vector<Compat1DFrameRec> log((size_t)SQ_FRAMES_MAX);
     CK(cudaMemcpy(log.data(), c->c_log_rec, sizeof(Compat1DFrameRec) * log.size(), cudaMemcpyDeviceToHost));
+    std::vector<double> xlog;
+    if (xavg && nframes > 0) {  // the whole log in one copy
+        xlog.resize((size_t)SQ_FRAMES_MAX * (size_t)N);
+        CK(cudaMemcpy(xlog.data(), c->c_log_xavg, sizeof(double) * xlog.size(), cudaMemcpyDeviceToHost));
+    }
     for (int k = 0; k < nframes; ++k) {
         const int slot = (int)((c->c_frames_done + k) % SQ_FRAMES_MAX);
         recs[k].dtau = log[(size_t)slot].dtau;
         recs[k].stable = log[(size_t)slot].stable;
         recs[k].steps = log[(size_t)slot].steps;
         if (xavg && log[(size_t)slot].stable)
-            CK(cudaMemcpy(xavg + (size_t)k * N, c->c_log_xavg + (size_t)slot * N, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost));
+            memcpy(xavg + (size_t)k * N, xlog.data() + (size_t)slot * N, sizeof(double) * (size_t)N);
     }
     c->c_frames_done += nframes;
     Compat1DCtl h{};
