@@ -145,6 +145,7 @@ def cpu_baseline(wl, seconds=12.0):
     V = int(np.prod(dims))
     o = O.LatticeOracle(dims, real=O.F32 if wl["real"] == "f32" else O.F64, potential=wl["pot"], m2=wl["m2"],
                         lam=wl["lam"])
+    cores = O.set_threads(len(os.sched_getaffinity(0)))
     o.step(wl["dtau"], 1, omp=True)  # warm-up (page faults, thread pool)
     t0 = time.perf_counter()
     o.step(wl["dtau"], 2, omp=True)
@@ -153,7 +154,6 @@ def cpu_baseline(wl, seconds=12.0):
     t0 = time.perf_counter()
     o.step(wl["dtau"], n, omp=True)
     dt = time.perf_counter() - t0
-    cores = len(os.sched_getaffinity(0))
     return {"value": V * n / dt, "unit": "site-updates/s", "cores": cores, "kind": "port",
             "sample": f"{n} tau-steps of the {'x'.join(map(str, dims))} lattice ({dt:.1f} s), oracle OpenMP port, "
                       f"{cores} threads"}, n, dt
@@ -171,6 +171,7 @@ def run_reference(args, wl, name):
     dims = wl["dims"]
     V = int(np.prod(dims))
     o = O.LatticeOracle(dims, real=O.F32 if wl["real"] == "f32" else O.F64, potential=wl["pot"], m2=wl["m2"], lam=wl["lam"])
+    cores = O.set_threads(len(os.sched_getaffinity(0)))  # torchrun sets OMP_NUM_THREADS=1: override
     o.step(wl["dtau"], 1, omp=True)
     t0 = time.perf_counter()
     o.step(wl["dtau"], 1, omp=True)
@@ -184,7 +185,6 @@ def run_reference(args, wl, name):
     for _ in range(args.steps):
         o.step(wl["dtau"], sample, omp=True)
     dt = time.perf_counter() - t0
-    cores = len(os.sched_getaffinity(0))
     val = V * sample * args.steps / dt
     line = {"impl": "reference", "metric": "lattice site-updates/s", "value": val, "unit": "site-updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -192,7 +192,7 @@ def run_reference(args, wl, name):
             "config": {"workload": name, "desc": wl["desc"], "dims": list(dims), "dtau": wl["dtau"],
                        "tau_steps_per_step": sample},
             "cpu_baseline": {"value": val, "unit": "site-updates/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} tau-steps per step instead of {wl['loops']}"},
+                             "sample": f"{sample} of the workload's {wl['loops']} tau-steps per step, oracle OpenMP port, {cores} threads"},
             "e2e": {"value": val, "unit": "site-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

@@ -83,6 +83,8 @@ def lib() -> C.CDLL:
         L.sqo_jump.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
         L.sqo_lattice_step.argtypes = [C.POINTER(Lattice), C.c_double]
         L.sqo_lattice_step_omp.argtypes = [C.POINTER(Lattice), C.c_double]
+        L.sqo_set_threads.argtypes = [C.c_int]
+        L.sqo_set_threads.restype = C.c_int
         L.sqo_lattice_draws.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64),
                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.sqo_write_endfile.restype = C.c_int
@@ -163,6 +165,12 @@ class Compat1D:
             self.s.omega = om0
             self.s.stable = 1
         return ok
+
+
+def set_threads(n: int = 0) -> int:
+    """OpenMP threads of LatticeOracle.step(omp=True); n <= 0 only queries.  bench.py's timing legs call
+    it with the process's CPU affinity because torchrun exports OMP_NUM_THREADS=1 to its workers."""
+    return int(lib().sqo_set_threads(int(n)))
 
 
 class LatticeOracle:

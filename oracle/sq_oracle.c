@@ -608,6 +608,19 @@ void sqo_lattice_step(sqo_lattice *L, double dtau)
     free(ss);
 }
 
+/* Thread count of sqo_lattice_step_omp.  torchrun exports OMP_NUM_THREADS=1 to its workers, so the
+ * timing legs of bench.py set the count explicitly (n <= 0: leave as is) and report what they got. */
+int sqo_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 void sqo_lattice_step_omp(sqo_lattice *L, double dtau)
 {
     const int64_t V = lat_volume(L);

@@ -131,6 +131,7 @@ typedef struct sqo_lattice {
 void sqo_lattice_step(sqo_lattice *L, double dtau);
 /* Same result computed with OpenMP + affine jump-ahead (CPU baseline). */
 void sqo_lattice_step_omp(sqo_lattice *L, double dtau);
+int sqo_set_threads(int n); /* n > 0: set the OpenMP thread count; returns the count in force */
 
 /* chain jump-ahead (independent of the product's implementation):
  * seed before the draw at gid g0+D given seed s before the draw at gid g0,

@@ -178,6 +178,20 @@ def test_lattice_omp_equals_serial(oracle, real, dims):
     assert np.allclose(a.slice_xx0, b.slice_xx0, rtol=0, atol=1e-14)
 
 
+def test_omp_thread_count_is_settable_and_result_independent(oracle):
+    """bench.py's CPU legs set the thread count themselves (torchrun exports OMP_NUM_THREADS=1);
+    the field does not depend on it."""
+    prev = oracle.set_threads(0)
+    outs = []
+    for n in (1, 2, 5):
+        assert oracle.set_threads(n) == n
+        o = oracle.LatticeOracle((16, 6, 10), real=oracle.F32, potential=4, m2=0.25, lam=0.5)
+        o.step(0.01, 4, omp=True)
+        outs.append((o.field.copy(), o.seed))
+    oracle.set_threads(prev)
+    assert all(np.array_equal(outs[0][0], f) and outs[0][1] == sd for f, sd in outs[1:])
+
+
 def test_lattice_event_replay_serial_vs_omp(oracle):
     """A seed that hits the inf-retry inside the lattice: both paths must agree (OMP falls back)."""
     # seed 177446488061229 retries at gid 0
