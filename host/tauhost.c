@@ -104,8 +104,8 @@ int main(int argc, char **argv)
         for (int k = 0; k < nb; ++k, ++j) {
             if (j % a.fps == 0) th_print_frame(stdout, n, xavg, recs[k].dtau, j, a.frames);
             if (recs[k].stable == 1) memcpy(xavg, xlog + (size_t)k * n, sizeof(double) * (size_t)n);
+            fflush(stdout); /* every frame, as the reference does (tauhost.c:558) */
         }
-        fflush(stdout);
     }
     free(xlog);
     if ((rc = sq_measure(ctx, &obs)) != SQ_OK) return fail_sq("sq_measure", rc); /* f, x, xx0, omega for the end file */

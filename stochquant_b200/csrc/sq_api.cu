@@ -101,7 +101,7 @@ extern "C" void sq_free(sq_ctx *c) {
                     c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps, c->c_ctl, c->c_log_rec, c->c_log_xavg,
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_partials2, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
-                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump,
+                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_nclamp_step, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump,
                     c->r_halo, c->r_error, c->r_progress, c->r_ckpt, c->r_hist_rows, c->r_hist_p2, c->r_step_sums};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -123,7 +123,8 @@ static int init_compat(sq_ctx *c, const double *f0, const double *x0, const doub
     if (p.ndim != 1 || p.real != SQ_REAL_F64) return SQ_ERR_INVALID;
     if (p.potential != SQ_POT_HARMONIC && p.potential != SQ_POT_DOUBLEWELL) return SQ_ERR_UNSUPPORTED;
     const int64_t N = p.dims[0];
-    if (N < 3 || N > 8191) return SQ_ERR_INVALID;
+    // the frame kernel keeps its whole state on chip: 56 N + 16 bytes of shared memory (sq_compat1d.cu)
+    if (N < 3 || N > 4096) return SQ_ERR_INVALID;
     int rc;
     double **arrs[] = {&c->c_f, &c->c_x, &c->c_xx0, &c->c_newf, &c->c_newx, &c->c_newxx0};
     for (auto a : arrs)
@@ -183,7 +184,8 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
         p.slab_t0 = 0;
         p.slab_nt = Lt;
     }
-    if (p.slab_t0 < 0 || p.slab_nt < 1 || p.slab_t0 + p.slab_nt > Lt || p.slab_nt > 65535) return SQ_ERR_INVALID;
+    // (grid.y = local slices; finalize_kernel reduces them in 16 nt bytes of shared memory)
+    if (p.slab_t0 < 0 || p.slab_nt < 1 || p.slab_t0 + p.slab_nt > Lt || p.slab_nt > FINALIZE_MAX_NT) return SQ_ERR_INVALID;
     if (p.slab_nt != Lt && p.nchains != 1) return SQ_ERR_INVALID;
     c->nt = (int)p.slab_nt;
     c->vlocal = c->vslice * c->nt;
@@ -246,6 +248,7 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
     if ((rc = dalloc(&c->l_lam, (size_t)p.nchains))) return rc;
     if ((rc = dalloc(&c->l_redbuf, 2 * 1024))) return rc;
     if ((rc = dalloc(&c->l_nclamped, 1))) return rc;
+    if ((rc = dalloc(&c->l_nclamp_step, MAX_SEQ_STEPS))) return rc;
     {  // jump coefficients that do not depend on the seed: slice starts and first strips
         std::vector<JumpEntry> sj((size_t)c->nt), qj((size_t)256 * c->ctas_per_slice);
         for (int t = 0; t < c->nt; ++t) sj[t] = jump_entry((u64)(p.slab_t0 + t) * (u64)c->vslice);
@@ -503,6 +506,7 @@ static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
         A.seed_out = c->l_seeds[b ^ 1];
         A.n_rebase = (k == 0) ? (int)c->entries.size() : 0;
         sq_fill_rebase_inline(A, c->entries.data(), A.n_rebase);
+        A.nclamped = c->l_nclamp_step + k;
         FinalizeArgs F{};
         F.nt = c->nt;
         F.nchains = p.nchains;
@@ -518,6 +522,7 @@ static int enqueue_lattice(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
         F.sums_mean = c->l_sums_mean;
         F.history = nullptr;
         F.event_key = c->l_event;
+        F.step_index = k;
         { int rs = sq_enqueue_step(c, A, F, k); if (rs) return rs; }
     }
     return sq_join_finalize(c);
@@ -721,6 +726,9 @@ static int sync_lattice(sq_ctx *c) {
         } else {
             int ok = n;
             if (key != NO_EVENT) ok = (int)(key >> KEY_STEP_SHIFT);
+            // clamp hits of the steps that stand (the event step is redone and counted then)
+            CK(launch_commit_clamps(c->l_nclamp_step, ok, n, c->l_nclamped, c->stream));
+            c->launches++;
             if (ok > 0) c->entries.clear();  // entries belonged to the batch's first step
             c->cur = (c->cur + ok) & 1;
             done += ok;

@@ -65,6 +65,7 @@ struct sq_ctx {
     double *l_partials = nullptr, *l_slice_sum = nullptr, *l_slice_x = nullptr, *l_slice_xx0 = nullptr,
            *l_sums = nullptr, *l_sums_mean = nullptr, *l_m2 = nullptr, *l_lam = nullptr, *l_redbuf = nullptr;
     unsigned long long *l_nclamped = nullptr;
+    unsigned long long *l_nclamp_step = nullptr;  // [MAX_SEQ_STEPS] clamp hits per step of the sequence in flight
     // observables off the critical path: finalize(n) runs on a side stream while update(n+1) runs;
     // the per-CTA partials are double-buffered, events order producer and consumer (sq_api.cu)
     double *l_partials2 = nullptr;

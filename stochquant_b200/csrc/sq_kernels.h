@@ -145,8 +145,15 @@ struct FinalizeArgs {
     double *sums_mean;   // [nchains][2]    running means of <phi>, <phi^2>
     double *history;     // slab mode: this step's [nt] slice sums + (sum phi, sum phi^2), else null
     const u64 *event_key;
+    int step_index;      // position of the step whose partials this reduces in the launch sequence
 };
+constexpr int FINALIZE_MAX_NT = 14000;  // 16 bytes of shared memory per local time slice
 cudaError_t launch_finalize(const FinalizeArgs &A, cudaStream_t stream);
+// Clamp hits are counted per step of a launch sequence (LatticeArgs::nclamped points at the step's slot):
+// a step that is replayed after an RNG event must not be counted twice.  total += sum of the first
+// nvalid slots; all ntotal slots are cleared for the next sequence.
+cudaError_t launch_commit_clamps(unsigned long long *slots, int nvalid, int ntotal, unsigned long long *total,
+                                 cudaStream_t stream);
 
 cudaError_t launch_debug_draws(u64 seed, u64 gid0, u64 n, const JumpEntry *jump, u64 *t1, u64 *t2,
                                cudaStream_t stream);

@@ -281,7 +281,11 @@ __global__ void __launch_bounds__(256, (REBASE || NDIM == 4 || sizeof(real) == 8
 // (tau_kernel.cl:144-145 at time-slice granularity; the host's xavg is derived in sq_measure)
 __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs A) {
     extern __shared__ double ssum[];  // [nt] slice sums, then [nt] phi^2 sums
-    if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;
+    // This runs on a side stream beside update(step_index + 1): an event raised by a LATER step must not
+    // drop this step's sample (the host keeps every step before the event step); only the event step
+    // itself and the launches behind it are void.
+    const u64 key = *((volatile const u64 *)A.event_key);
+    if (key != NO_EVENT && (int)(key >> KEY_STEP_SHIFT) <= A.step_index) return;
     const int chain = blockIdx.x;
     double *s1 = ssum, *s2 = ssum + A.nt;
     for (int t = threadIdx.x; t < A.nt; t += blockDim.x) {
@@ -321,7 +325,40 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs A) {
 }
 
 cudaError_t launch_finalize(const FinalizeArgs &A, cudaStream_t stream) {
-    finalize_kernel<<<A.nchains, 256, sizeof(double) * 2 * (size_t)A.nt, stream>>>(A);
+    const size_t smem = sizeof(double) * 2 * (size_t)A.nt;
+    if (A.nt > FINALIZE_MAX_NT) return cudaErrorInvalidValue;  // rejected at sq_init
+    if (smem > 48 * 1024) {
+        static size_t granted = 0;  // (grows monotonically; a racing second thread sets the same attribute)
+        if (smem > granted) {
+            cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            granted = smem;
+        }
+    }
+    finalize_kernel<<<A.nchains, 256, smem, stream>>>(A);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) commit_clamps_kernel(unsigned long long *slots, int nvalid, int ntotal, unsigned long long *total) {
+    __shared__ unsigned long long red[8];
+    unsigned long long a = 0;
+    for (int i = threadIdx.x; i < ntotal; i += blockDim.x) {
+        if (i < nvalid) a += slots[i];
+        slots[i] = 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) a += red[k];
+        if (a) *total += a;
+    }
+}
+cudaError_t launch_commit_clamps(unsigned long long *slots, int nvalid, int ntotal, unsigned long long *total,
+                                 cudaStream_t stream) {
+    if (ntotal <= 0) return cudaSuccess;
+    commit_clamps_kernel<<<1, 256, 0, stream>>>(slots, nvalid, ntotal, total);
     return cudaGetLastError();
 }
 
@@ -352,6 +389,7 @@ static cudaError_t preload_nd(int ndim) {
     if (ndim == 3) { touch((const void *)lattice_step_kernel<real, MATH, 3, false>); touch((const void *)lattice_step_kernel<real, MATH, 3, true>); }
     if (ndim == 4) { touch((const void *)lattice_step_kernel<real, MATH, 4, false>); touch((const void *)lattice_step_kernel<real, MATH, 4, true>); }
     touch((const void *)finalize_kernel);
+    touch((const void *)commit_clamps_kernel);
     return e;
 }
 cudaError_t preload_lattice_step(int real, int math, int ndim) {

@@ -53,16 +53,35 @@ extern "C" int sq_session_open(sq_session **out, const char *name, int rank, int
     }
     s->shm = (SessionShm *)p;
     uint32_t expect = 0;
-    if (!s->shm->nranks.compare_exchange_strong(expect, (uint32_t)nranks) && expect != (uint32_t)nranks) {
+    timespec rt;
+    clock_gettime(CLOCK_REALTIME, &rt);
+    const uint64_t now_ns = (uint64_t)rt.tv_sec * 1000000000ull + (uint64_t)rt.tv_nsec;
+    bool bad = false;
+    if (s->shm->nranks.compare_exchange_strong(expect, (uint32_t)nranks)) {
+        s->shm->created_ns.store(now_ns, std::memory_order_release);  // this rank created the ring
+    } else {
+        bad = expect != (uint32_t)nranks;  // ranks disagree on the ring size
+        // A live ring's name disappears as soon as every rank has attached.  A segment that a rank has
+        // already left, that was aborted, or that is older than a barrier would wait is the debris of a
+        // crashed open: its barrier counters cannot be trusted.
+        uint64_t born = 0;
+        for (int spin = 0; spin < 2000 && !(born = s->shm->created_ns.load(std::memory_order_acquire)); ++spin) usleep(100);
+        bad |= s->shm->closed.load(std::memory_order_acquire) != 0 || s->shm->abort_flag.load(std::memory_order_acquire) != 0;
+        bad |= born == 0 || (now_ns > born && (double)(now_ns - born) * 1e-9 > s->timeout_s);
+    }
+    if (bad) {
         munmap(p, sizeof(SessionShm));
         close(s->fd);
         delete s;
-        return SQ_ERR_INVALID;  // ranks disagree on the ring size (or a stale segment of that name)
+        return SQ_ERR_INVALID;
     }
     *out = s;
     // everybody is attached after this barrier: the name can go, the mapping stays
     int rc = sq_session_barrier(s);
-    if (rc == SQ_OK && rank == 0) shm_unlink(s->name);
+    if (rc == SQ_OK && rank == 0) {
+        shm_unlink(s->name);
+        s->unlinked = true;
+    }
     if (rc != SQ_OK) {
         sq_session_close(s);
         *out = nullptr;
@@ -129,6 +148,7 @@ extern "C" void sq_session_close(sq_session *s) {
         munmap(s->shm, sizeof(SessionShm));
     }
     if (s->fd >= 0) close(s->fd);
-    if (s->rank == 0) shm_unlink(s->name);  // in case open failed before the unlink
+    // only when open failed before the unlink: afterwards the name may belong to a NEW ring
+    if (s->rank == 0 && !s->unlinked) shm_unlink(s->name);
     delete s;
 }

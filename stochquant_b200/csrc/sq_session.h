@@ -31,7 +31,10 @@ struct SessionShm {
     std::atomic<uint32_t> generation;  // barrier sense
     std::atomic<uint32_t> abort_flag;  // raised by any rank that fails: wakes every waiter
     std::atomic<uint32_t> closed;      // ranks that left
-    uint32_t pad[11];
+    uint32_t pad0;
+    std::atomic<uint64_t> created_ns;  // CLOCK_REALTIME of the creating rank: a segment older than the barrier
+                                       // timeout that is still linked was left behind by a crashed open
+    uint32_t pad[8];
     SessionRankSlot slot[SESSION_MAX_RANKS];
 };
 
@@ -43,6 +46,7 @@ struct sq_session {
     int rank = 0, nranks = 1;
     int fd = -1;
     unsigned xchg = 0;  // exchange counter (mailbox parity)
+    bool unlinked = false;  // rank 0: the name was removed after the open barrier
     char name[128] = "";
     double timeout_s = 120.0;
 };

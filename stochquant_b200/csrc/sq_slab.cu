@@ -424,6 +424,7 @@ int sq_slab_enqueue(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
         LatticeArgs A = sq_lattice_args(c, dtau, k);
         A.n_rebase = (int)entries.size();
         sq_fill_rebase_inline(A, entries.data(), A.n_rebase);
+        A.nclamped = c->l_nclamp_step + k;
         A.wrap_time = 0;
         const unsigned Tw = T0 + (unsigned)k, Tp = Tw + 1u;
         const int pw = (int)(Tw & 1u), pp = (int)(Tp & 1u);
@@ -455,10 +456,13 @@ int sq_slab_enqueue(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
         F.sums_mean = c->l_sums_mean;
         F.history = sl->d_hist + (size_t)k * (size_t)(nt + 2);
         F.event_key = c->l_event;
+        F.step_index = k;
         if ((rc = sq_enqueue_step(c, A, F, k))) return rc;
         S = S_next;
     }
     sl->seed = S;
+    CK(launch_commit_clamps(c->l_nclamp_step, nsteps, nsteps, c->l_nclamped, c->stream));
+    c->launches++;
     return sq_join_finalize(c);
 }
 
