@@ -102,7 +102,7 @@ extern "C" void sq_free(sq_ctx *c) {
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_partials2, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
                     c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_nclamp_step, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump,
-                    c->r_halo, c->r_error, c->r_progress, c->r_ckpt, c->r_hist_rows, c->r_hist_p2, c->r_step_sums};
+                    c->r_halo, c->r_error, c->r_progress, c->r_ckpt, c->r_hist_rows, c->r_hist_p2, c->r_step_sums, c->r_nclamp_slots};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -290,9 +290,16 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
         const bool shape_ok = p.ndim == 2 && p.real == SQ_REAL_F32 && p.nchains == 1 && c->nt == Lt &&
                               L0 % 128 == 0 && L0 <= 1024 && !(p.flags & (SQ_FLAG_FORCE_STREAMING | SQ_FLAG_NO_OBSERVABLES));
         if (coop && shape_ok && sms > 0) {
-            const int nb = (int)std::min<int64_t>(sms, L1);
-            const int rows = (int)((L1 + nb - 1) / nb);
-            if (rows <= RES_MAX_ROWS) {
+            int nb = (int)std::min<int64_t>(sms, L1);
+            int rows = (int)((L1 + nb - 1) / nb);
+            static const bool force_v1 = getenv("SQ_RESIDENT_V1") != nullptr;  // A/B knob: the round-1 band kernel
+            {   // the row-parallel kernel wants bands of at least two rows (each edge row has ONE neighbour CTA)
+                const int nb2 = (int)std::min<int64_t>(sms, L1 / 2);
+                const int rows2 = nb2 > 0 ? (int)((L1 + nb2 - 1) / nb2) : 0;
+                c->res_v2 = !force_v1 && nb2 > 0 && rowres_strip((int)L0, rows2) != 0;
+                if (c->res_v2) { nb = nb2; rows = rows2; }
+            }
+            if (c->res_v2 || rows <= RES_MAX_ROWS) {
                 CK(preload_lattice_step(p.real, p.math, p.ndim));  // the event-recovery path: see sq_lattice.cu
                 c->res_ok = true;
                 c->res_nb = nb;
@@ -302,7 +309,8 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
                 if ((rc = dalloc(&c->r_progress, (size_t)nb))) return rc;
                 if ((rc = dalloc(&c->r_ckpt, 3 * (size_t)c->V))) return rc;
                 if ((rc = dalloc(&c->r_hist_rows, (size_t)RES_MAX_STEPS * (size_t)L1))) return rc;
-                if ((rc = dalloc(&c->r_hist_p2, (size_t)RES_MAX_STEPS * (size_t)nb))) return rc;
+                if ((rc = dalloc(&c->r_hist_p2, (size_t)RES_MAX_STEPS * (size_t)std::max<int64_t>(nb, L1)))) return rc;
+                if ((rc = dalloc(&c->r_nclamp_slots, (size_t)RES_SLOTS))) return rc;
                 if ((rc = dalloc(&c->r_step_sums, (size_t)RES_MAX_STEPS * 2))) return rc;
             }
         }
@@ -574,8 +582,11 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     // per-chain couplings live in device arrays for the streaming kernel; the resident kernel is
     // single-chain and takes them by value: keep both in sync through sq_set_chain (host mirror)
     if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
+    A.rows_max = c->res_rows;
+    A.nclamp_slots = c->r_nclamp_slots;
     static const int strip_w = getenv("SQ_RESIDENT_STRIP") ? atoi(getenv("SQ_RESIDENT_STRIP")) : 0;  // tuning knob
-    CK(launch_resident2d(A, p.math, c->res_nb, c->res_rows, strip_w, c->stream));
+    if (c->res_v2) CK(launch_rowres(A, p.math, c->res_nb, c->stream));
+    else CK(launch_resident2d(A, p.math, c->res_nb, c->res_rows, strip_w, c->stream));
     if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     c->launches++;
     return enqueue_resident_welford(c, nsteps, runs0);
@@ -588,7 +599,7 @@ static int enqueue_resident_welford(sq_ctx *c, int nsteps, int64_t runs0) {
     W.nt = c->nt;
     W.nsteps = nsteps;
     W.tmid = (int)(p.dims[1] / 2);
-    W.np2 = c->res_nb;
+    W.np2 = c->res_v2 ? (int)p.dims[1] : c->res_nb;  // partial sums of phi^2: per row | per CTA
     W.vslice = c->vslice;
     W.runs = runs0;
     W.hist_rows = c->r_hist_rows;
@@ -601,6 +612,10 @@ static int enqueue_resident_welford(sq_ctx *c, int nsteps, int64_t runs0) {
     W.event_key = c->l_event;
     CK(launch_welford_history(W, c->r_step_sums, c->stream));
     c->launches += 2;
+    if (c->res_v2) {  // clamp hits of the checkpoint intervals that stand (none of them while an event is flagged)
+        CK(launch_commit_clamps(c->r_nclamp_slots, (nsteps + RES_CKPT - 1) / RES_CKPT, RES_SLOTS, c->l_nclamped, c->l_event, c->stream));
+        c->launches++;
+    }
     return SQ_OK;
 }
 
@@ -719,6 +734,9 @@ static int sync_lattice(sq_ctx *c) {
                     done += c0;
                     runs0 += c0;
                     k -= c0;
+                } else if (c->res_v2) {  // nothing stands: drop the abandoned launch's clamp counts
+                    CK(launch_commit_clamps(c->r_nclamp_slots, 0, RES_SLOTS, c->l_nclamped, nullptr, c->stream));
+                    c->launches++;
                 }
                 if (k > 0) c->res_limit = k;
                 else c->force_stream = 1;
@@ -727,7 +745,7 @@ static int sync_lattice(sq_ctx *c) {
             int ok = n;
             if (key != NO_EVENT) ok = (int)(key >> KEY_STEP_SHIFT);
             // clamp hits of the steps that stand (the event step is redone and counted then)
-            CK(launch_commit_clamps(c->l_nclamp_step, ok, n, c->l_nclamped, c->stream));
+            CK(launch_commit_clamps(c->l_nclamp_step, ok, n, c->l_nclamped, nullptr, c->stream));
             c->launches++;
             if (ok > 0) c->entries.clear();  // entries belonged to the batch's first step
             c->cur = (c->cur + ok) & 1;

@@ -83,7 +83,9 @@ struct sq_ctx {
     JumpEntry *l_cta_jump = nullptr, *l_thr_jump = nullptr;
     // resident 2-D path (sq_resident.cu)
     bool res_ok = false;
+    bool res_v2 = false;    // row-parallel kernel (sq_rowres.cu); false: the round-1 band kernel (sq_resident.cu)
     int res_nb = 0, res_rows = 0;
+    unsigned long long *r_nclamp_slots = nullptr;  // [RES_SLOTS] clamp hits per checkpoint interval of a resident launch
     unsigned long long *r_halo = nullptr;
     unsigned *r_error = nullptr, *r_progress = nullptr;
     float *r_ckpt = nullptr;  // [3][V] checkpoints of the resident kernel (RNG-event recovery)

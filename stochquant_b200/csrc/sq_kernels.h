@@ -153,7 +153,7 @@ cudaError_t launch_finalize(const FinalizeArgs &A, cudaStream_t stream);
 // a step that is replayed after an RNG event must not be counted twice.  total += sum of the first
 // nvalid slots; all ntotal slots are cleared for the next sequence.
 cudaError_t launch_commit_clamps(unsigned long long *slots, int nvalid, int ntotal, unsigned long long *total,
-                                 cudaStream_t stream);
+                                 const u64 *event_key /* null, or: do nothing while an event is flagged */, cudaStream_t stream);
 
 cudaError_t launch_debug_draws(u64 seed, u64 gid0, u64 n, const JumpEntry *jump, u64 *t1, u64 *t2,
                                cudaStream_t stream);
@@ -187,8 +187,15 @@ struct ResidentArgs {
     unsigned one;         // 1, from the host: a multiplier ptxas cannot fold (sq_site.cuh: site_const_next)
     float *ckpt;          // [3][L1][L0]
     unsigned *progress;   // [nblocks] steps completed by each CTA when it left
+    // ---- row-parallel kernel (sq_rowres.cu) ----
+    int rows_max;                       // rows per CTA (ceil(L1 / nblocks))
+    unsigned long long *nclamp_slots;   // [RES_SLOTS] clamp hits per interval of RES_CKPT steps (committed for the
+                                        // intervals that stand: an abandoned launch must not count twice)
 };
 constexpr int RES_CKPT = 128;
+constexpr int RES_SLOTS = 16;  // RES_MAX_STEPS / RES_CKPT
+int rowres_strip(int L0, int rows_max);  // sites per thread (8 | 4), 0: shape not eligible
+cudaError_t launch_rowres(const ResidentArgs &A, int math, int nblocks, cudaStream_t st);
 cudaError_t launch_resident2d(const ResidentArgs &A, int math, int nblocks, int rows_max, int strip_w, cudaStream_t st);
 
 struct WelfordArgs {

@@ -339,8 +339,10 @@ cudaError_t launch_finalize(const FinalizeArgs &A, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256) commit_clamps_kernel(unsigned long long *slots, int nvalid, int ntotal, unsigned long long *total) {
+__global__ void __launch_bounds__(256) commit_clamps_kernel(unsigned long long *slots, int nvalid, int ntotal, unsigned long long *total,
+                                                            const u64 *event_key) {
     __shared__ unsigned long long red[8];
+    if (event_key && *((volatile const u64 *)event_key) != NO_EVENT) return;  // the host commits after the recovery
     unsigned long long a = 0;
     for (int i = threadIdx.x; i < ntotal; i += blockDim.x) {
         if (i < nvalid) a += slots[i];
@@ -356,9 +358,9 @@ __global__ void __launch_bounds__(256) commit_clamps_kernel(unsigned long long *
     }
 }
 cudaError_t launch_commit_clamps(unsigned long long *slots, int nvalid, int ntotal, unsigned long long *total,
-                                 cudaStream_t stream) {
+                                 const u64 *event_key, cudaStream_t stream) {
     if (ntotal <= 0) return cudaSuccess;
-    commit_clamps_kernel<<<1, 256, 0, stream>>>(slots, nvalid, ntotal, total);
+    commit_clamps_kernel<<<1, 256, 0, stream>>>(slots, nvalid, ntotal, total, event_key);
     return cudaGetLastError();
 }
 

@@ -461,7 +461,7 @@ int sq_slab_enqueue(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
         S = S_next;
     }
     sl->seed = S;
-    CK(launch_commit_clamps(c->l_nclamp_step, nsteps, nsteps, c->l_nclamped, c->stream));
+    CK(launch_commit_clamps(c->l_nclamp_step, nsteps, nsteps, c->l_nclamped, nullptr, c->stream));
     c->launches++;
     return sq_join_finalize(c);
 }
