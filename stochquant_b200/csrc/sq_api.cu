@@ -102,7 +102,7 @@ extern "C" void sq_free(sq_ctx *c) {
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_partials2, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
                     c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_nclamp_step, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump,
-                    c->r_halo, c->r_error, c->r_progress, c->r_ckpt, c->r_hist_rows, c->r_hist_p2, c->r_step_sums, c->r_nclamp_slots};
+                    c->r_halo, c->r_error, c->r_progress, c->r_ckpt, c->r_hist_rows, c->r_step_sums, c->r_nclamp_slots};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -308,8 +308,9 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
                 if ((rc = dalloc(&c->r_error, 1))) return rc;
                 if ((rc = dalloc(&c->r_progress, (size_t)nb))) return rc;
                 if ((rc = dalloc(&c->r_ckpt, 3 * (size_t)c->V))) return rc;
-                if ((rc = dalloc(&c->r_hist_rows, (size_t)RES_MAX_STEPS * (size_t)L1))) return rc;
-                if ((rc = dalloc(&c->r_hist_p2, (size_t)RES_MAX_STEPS * (size_t)std::max<int64_t>(nb, L1)))) return rc;
+                // one allocation: hist_rows[RES_MAX_STEPS][L1], then hist_p2 (per row for the row-parallel kernel, per CTA before)
+                if ((rc = dalloc(&c->r_hist_rows, 2 * (size_t)RES_MAX_STEPS * (size_t)L1))) return rc;
+                c->r_hist_p2 = c->r_hist_rows + (size_t)RES_MAX_STEPS * (size_t)L1;
                 if ((rc = dalloc(&c->r_nclamp_slots, (size_t)RES_SLOTS))) return rc;
                 if ((rc = dalloc(&c->r_step_sums, (size_t)RES_MAX_STEPS * 2))) return rc;
             }
@@ -583,6 +584,8 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     // single-chain and takes them by value: keep both in sync through sq_set_chain (host mirror)
     if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     A.rows_max = c->res_rows;
+    static const int dbg = getenv("SQ_ROWRES_DEBUG") ? atoi(getenv("SQ_ROWRES_DEBUG")) : 0;  // timing experiments (wrong results)
+    A.debug = dbg;
     A.nclamp_slots = c->r_nclamp_slots;
     static const int strip_w = getenv("SQ_RESIDENT_STRIP") ? atoi(getenv("SQ_RESIDENT_STRIP")) : 0;  // tuning knob
     if (c->res_v2) CK(launch_rowres(A, p.math, c->res_nb, c->stream));

@@ -26,6 +26,7 @@
 // (step, gid) is raised with atomicMin, every CTA leaves, the host resumes from the last checkpoint every
 // CTA has written (sq_api.cu).  Waits are bounded and abort-aware.
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "sq_kernels.h"
 #include "sq_site.cuh"
@@ -96,6 +97,11 @@ __device__ __forceinline__ unsigned lds_f32_bits(unsigned a) {
     return v;
 }
 __device__ __forceinline__ void sts_u32(unsigned a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ u64 lds_u64(unsigned a) {
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
 __device__ __forceinline__ void sts_u64(unsigned a, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
 __device__ __forceinline__ float4 lds_f4(unsigned a) {
     float4 v;
@@ -165,6 +171,7 @@ __device__ __noinline__ void checkpoint4_cold(float *dst, pair_t a, pair_t b) {
 //            talk to the neighbour CTAs through the halo words
 //   REDUCER  one warp per (row, kind) turns the row-sum partials into the per-step history; the first of them also
 //            polls the event word and (CTA 0) draws for the omega work-item
+constexpr int RES_MAX_STEPS_K = 2048;  // = RES_MAX_STEPS (sq_ctx.h): hist_p2 = hist_rows + RES_MAX_STEPS_K * L1
 constexpr int ROWRES_THREADS = 896;  // 7 rows x 128 strips for 1024^2; 72 registers per thread
 
 struct RowGeo {
@@ -190,7 +197,7 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
     const unsigned rs_base = G.smem_base + 2u * parb;                   // rs[2 parity][2 kind][NRM][TPR] floats
     const unsigned rsk = (unsigned)(NRM * TPR) * 4u;                    // bytes between the two kinds
     const unsigned a_rs = rs_base + (unsigned)(k * TPR + j) * 4u;
-    const unsigned a_chain = G.chain_a + (unsigned)tid * 16u;           // {T, K2} ; + 16 blockDim: {c1_0, c2_0}
+    const unsigned a_chain = G.chain_a + (unsigned)tid * 16u;           // {T, K2} ; + 16 blockDim: {c1_0, c2_0} ; + 32 blockDim: role slot
     const unsigned chain_pl = (unsigned)blockDim.x * 16u;
 
     // halo words: [parity][CTA][first | last][L0]; only the edge rows' warps touch them
@@ -258,34 +265,43 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
     };
 
     // ---- reducer duties ------------------------------------------------------------------------------
-    const int nw = (nr * TPR) >> 5, wid = tid >> 5;
-    // this warp's first item (row = wid / 2, kind = wid % 2): its shared-memory source (parity 0) and where its history
-    // entries go.  A lane covers 4 partials per 128 threads of the row (TPR <= 256); lanes beyond the row read a valid
-    // address and are masked.
-    const bool red_lane = 4 * lane < TPR;
-    const unsigned red_src = rs_base + (unsigned)(wid & 1) * rsk + (unsigned)((wid >> 1) * TPR + (red_lane ? 4 * lane : 0)) * 4u;
-    const float red_mask = red_lane ? 1.0f : 0.0f;
-    double *red_dst = ((wid & 1) ? A.hist_p2 : A.hist_rows) + r0 + (wid >> 1);
+    // A reducer warp's first item is (row = wid / 2, kind = wid % 2).  What it needs every step -- its shared-memory
+    // source (parity 0), the word offset of its history entry, the mask of lanes beyond the row (a lane covers 4
+    // partials per 128 threads of the row) -- sits in the thread's role slot in shared memory: registers are what this
+    // loop is short of, and ptxas would otherwise re-derive all of it from %tid every step.
+    const int nw = (nr * TPR) >> 5;
+    if (REDUCER) {
+        const int wid = tid >> 5;
+        const bool red_lane = 4 * lane < TPR;
+        const unsigned red_src = rs_base + (unsigned)(wid & 1) * rsk + (unsigned)((wid >> 1) * TPR + (red_lane ? 4 * lane : 0)) * 4u;
+        const unsigned red_off = (unsigned)(wid & 1) * (unsigned)RES_MAX_STEPS_K * (unsigned)A.L1 + (unsigned)(r0 + (wid >> 1));
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_chain + 2u * chain_pl), "r"(red_src), "r"(red_off),
+                     "r"(__float_as_uint(red_lane ? 1.0f : 0.0f)), "r"((unsigned)wid + (unsigned)nw) : "memory");
+    }
     auto reduce_rows = [&](int step, unsigned parity) {
+        unsigned red_src, red_off, red_mask, red_next;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(red_src), "=r"(red_off), "=r"(red_mask), "=r"(red_next) : "r"(a_chain + 2u * chain_pl));
         const float4 v = lds_f4(red_src + parity * 2u * rsk);
-        float a = ((v.x + v.y) + (v.z + v.w)) * red_mask;
+        float a = ((v.x + v.y) + (v.z + v.w)) * __uint_as_float(red_mask);
         if (TPR > 128) {  // (uniform) rows of more than 128 strips: a second chunk per lane
             const float4 w = lds_f4(red_src + parity * 2u * rsk + 512u);
             a += (4 * lane + 128 < TPR) ? (w.x + w.y) + (w.z + w.w) : 0.f;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) red_dst[(size_t)step * A.L1] = (double)a;
-        if (nw < 2 * nr) reduce_rows_general(A.hist_rows, A.hist_p2, A.L1, rs_base + parity * 2u * rsk, rsk, TPR, wid + nw, nw, nr, r0, step, lane);  // (uniform) fewer warps than items
+        if (lane == 0) A.hist_rows[red_off + (unsigned)step * (unsigned)A.L1] = (double)a;  // (hist_p2 follows hist_rows)
+        if (nw < 2 * nr)  // (uniform) fewer warps than items: the general walk
+            reduce_rows_general(A.hist_rows, A.hist_p2, A.L1, rs_base + parity * 2u * rsk, rsk, TPR, (int)red_next, nw, nr, r0, step, lane);
     };
-    // service lane (first reducer warp): event-word poll; CTA 0: the omega work-item's draws
-    const bool svc_lane = REDUCER && wid == 0 && lane == 0, omega_lane = svc_lane && b == 0;
+    // service lane (first reducer warp): event-word poll; CTA 0: the omega work-item's draws, whose running
+    // step-start seed lives in shared memory too.
+    const bool svc_lane = REDUCER && tid == 0, omega_lane = svc_lane && b == 0;
+    const unsigned a_svc = G.flags_a + 8u;
+    if (svc_lane) sts_u64(a_svc, omega_lane ? A.seed_in[0] : 0ull);
 
     unsigned myclamp = 0, failed = 0;
     pair_t NZ[NP];
     noise_phase(NZ, A.step_index0);
-    u64 S_om = 0, ek = NO_EVENT;  // service lane: step-start seed of the omega draws; the event word as read one step ago
-    if (omega_lane) S_om = A.seed_in[0];
 
     // first barrier phase: everybody's initial row is in rowbuf[0]
     __syncwarp();
@@ -311,10 +327,8 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
             }
             if (fl) break;
         }
-        if (REDUCER && svc_lane) {
-            if (ek != NO_EVENT) sts_u32(flags_a + (par ^ 1u) * 4u, 1u);  // seen one step ago: everybody leaves at the top of the next step
-            ek = *((volatile const u64 *)A.event_key);
-        }
+        u64 ek = NO_EVENT;  // service lane: the event word, requested here and looked at after the stencil phase
+        if (REDUCER && svc_lane) ek = *((volatile const u64 *)A.event_key);
 
         // ---- stencil phase: neighbours of the field before step n -----------------------------------------
         const unsigned a_cur = a_own + par * parb, a_nxt = a_own + (par ^ 1u) * parb;
@@ -348,7 +362,7 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
 #pragma unroll
                     for (int i = 0; i < NP; ++i)
                         ok &= ((unsigned)(pre[i].x >> 32) == want) & ((unsigned)(pre[i].y >> 32) == want);
-                    if (__builtin_expect(ok, 1)) break;
+                    if (__builtin_expect(ok | (A.debug & 1), 1)) break;
                     ++spins;
                     // the launch is being abandoned (an RNG event must be replayed) or the neighbour is lost (never
                     // hang the GPU): stop waiting; what this step computes from here on is void
@@ -434,17 +448,18 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
 #pragma unroll
             for (int i = 0; i < NP; ++i) st_words(ho + 2 * i, word_of(a[2 * i], tag), word_of(a[2 * i + 1], tag));
         }
+        if (REDUCER && svc_lane && ek != NO_EVENT) sts_u32(flags_a + (par ^ 1u) * 4u, 1u);  // everybody leaves at the top of the next step
         __syncwarp();
         if (lane == 0) mbar_arrive(mbar);
 
         // ---- independent of every other thread: the omega work-item's draw, the next step's noise --------------
         if (REDUCER && omega_lane) {  // gid = V, tau_kernel.cl:103-110
-            const u64 sV = lcg_apply(A.vol_jump, S_om, 0) & LCG_MASK;
+            const u64 sV = lcg_apply(A.vol_jump, lds_u64(a_svc), 0) & LCG_MASK;
             u64 t1, t2;
             lcg_draw(sV, (u64)A.V, t1, t2);
             if (lcg_event(sV, t1, t2)) atomicMin((unsigned long long *)A.event_key, event_key(A.step_index0 + n, 0, (u64)A.V));
-            S_om = lcg_next_seed(t2);
-            if (!more) A.seed_out[0] = S_om;
+            sts_u64(a_svc, lcg_next_seed(t2));
+            if (!more) A.seed_out[0] = lcg_next_seed(t2);
         }
         if (more) {
             noise_phase(NZ, A.step_index0 + n + 1);
@@ -456,7 +471,7 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
                 for (int i = 0; i < NP; ++i) pre[i] = ld_words(ps + 2 * i);
             }
         }
-        mbar_wait(mbar, (unsigned)(n + 1) & 1u);
+        if (!(A.debug & 2)) mbar_wait(mbar, (unsigned)(n + 1) & 1u);
     }
     if (n == A.nsteps) {  // went through: the last step's sums, and was the last step void?
         const unsigned fl = lds_f32_bits(flags_a + ((unsigned)n & 1u) * 4u);
@@ -493,10 +508,10 @@ __global__ void __launch_bounds__(ROWRES_THREADS, 1) rowres_kernel(const Residen
     G.j = tid - kk * TPR;
     G.k = (kk >= G.nr) ? kk : ((kk == G.nr - 1) ? G.nr - 1 : ((kk == G.nr - 2) ? 0 : kk + 1));
 
-    // shared: rowbuf[2][NRM][L0] | rs[2][2][NRM][TPR] | chain[2][threads] x 16 B | mbarrier | flags[2]
+    // shared: rowbuf[2][NRM][L0] | rs[2][2][NRM][TPR] | chain[3][threads] x 16 B | mbarrier | flags[2] | service state
     G.smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
     G.chain_a = G.smem_base + (unsigned)(2 * NRM * L0 + 4 * NRM * TPR) * 4u;
-    G.mbar = G.chain_a + (unsigned)blockDim.x * 32u;
+    G.mbar = G.chain_a + (unsigned)blockDim.x * 48u;
     G.flags_a = G.mbar + 8u;
     // flags[step parity]: bit 0 leave, bit 1 the step in flight is void; written during step n for step n+1, read at
     // the top of a step after the barrier phase that orders them -- every thread of the CTA takes the same decision
@@ -554,7 +569,7 @@ static cudaError_t launch_rowres_mp(const ResidentArgs &A, int nblocks, cudaStre
     const int w = rowres_strip(A.L0, A.rows_max);
     if (!w || A.L1 < 2 * nblocks) return cudaErrorInvalidValue;
     const int tpr = A.L0 / w, threads = A.rows_max * tpr;
-    const size_t smem = sizeof(float) * ((size_t)2 * A.rows_max * A.L0 + (size_t)4 * A.rows_max * tpr) + (size_t)threads * 32 + 32;
+    const size_t smem = sizeof(float) * ((size_t)2 * A.rows_max * A.L0 + (size_t)4 * A.rows_max * tpr) + (size_t)threads * 48 + 64;
     return w == 8 ? launch_rowres_np<MATH, POT, 4>(A, nblocks, threads, smem, st) : launch_rowres_np<MATH, POT, 2>(A, nblocks, threads, smem, st);
 }
 
@@ -562,6 +577,8 @@ static cudaError_t launch_rowres_mp(const ResidentArgs &A, int nblocks, cudaStre
 // shape does not fit (more than ROWRES_THREADS threads)
 int rowres_strip(int L0, int rows_max) {
     if (L0 % 128 != 0 || L0 > 1024 || rows_max < 2) return 0;
+    // (16 sites per thread -- 14 warps per SM with 127 registers -- was measured at 188 G site-updates/s against 470:
+    // the code of six role loops no longer fits the instruction caches and half the warps hide half the latency)
     if (L0 % 256 == 0 && rows_max * (L0 / 8) <= ROWRES_THREADS) return 8;
     if (rows_max * (L0 / 4) <= ROWRES_THREADS) return 4;
     return 0;
