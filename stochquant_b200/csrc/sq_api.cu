@@ -201,12 +201,26 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
             const int64_t rg = 256 / tpr, nrows = c->vslice / L0;
             int best = 0;
             static const int force_R = getenv("SQ_MARCH_R") ? atoi(getenv("SQ_MARCH_R")) : 0;  // tuning knob
-            for (int R = force_R ? force_R : 16; R >= 1; R >>= 1) {
-                if (L1 % R != 0 || nrows % (rg * R) != 0) continue;
-                if (!best) best = R;  // the largest that fits ...
-                const int64_t ctas = nrows / (rg * R) * c->nt * p.nchains;
-                if (ctas >= 148 * 12) { best = R; break; }  // ... unless a smaller one is needed to fill the GPU
-                best = R;
+            // The tile kernel is correct (the whole GPU suite passes on it) and executes fewer instructions (50 against 58
+            // per site) but is SLOWER than the marching kernel on every measured shape (256^3 slices 334 against 375 G
+            // site-updates/s, 64^4 287 / 305, 32^4 chains 264 / 300): 24 instead of 32 warps per SM, a staging bubble at
+            // the start of every CTA and four global streams with one pass of lookahead.  It is kept behind SQ_TILE=1
+            // for the next round's persistent / multi-stage version; the marching kernel is the default.
+            static const bool no_tile = getenv("SQ_TILE") == nullptr;
+            int tlog = 0;
+            while ((1 << tlog) < tpr) tlog++;
+            // the tile kernel (sq_tile.cu) stages a CTA's rows in shared memory: 4, 8 or 16 rows per thread, tiles that are
+            // whole planes or divide one, at most 72 KB; otherwise the marching kernel takes the shape
+            for (int pass = no_tile ? 1 : 0; pass < 2 && !best; ++pass) {
+                const bool tile = pass == 0;
+                for (int R = force_R ? force_R : 16; R >= 1; R >>= 1) {
+                    if (L1 % R != 0 || nrows % (rg * R) != 0) continue;
+                    if (tile && !tile_shape_ok((int)L0, (int)L1, tlog, R)) continue;
+                    const int64_t ctas = nrows / (rg * R) * c->nt * p.nchains;
+                    best = R;  // the largest that fits, unless a smaller one is needed to fill the GPU
+                    if (ctas >= 148 * 12) break;
+                }
+                c->tile_ok = tile && best != 0;
             }
             if (best && nrows / (rg * best) <= 65535) {
                 c->march_ok = true;
@@ -450,7 +464,10 @@ LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */
     A.stride_jump = jump_entry((u64)A.strips_per_cta_iter * (u64)vec);
     A.vol_jump = jump_entry((u64)c->V);
     A.jump = c->d_jump;
-    A.m_on = c->march_ok ? 1 : 0;
+    A.m_on = c->march_ok ? (c->tile_ok ? 2 : 1) : 0;
+    A.t_dck = LCG_BETA * (u64)p.dims[0] * jump_entry((u64)p.dims[0]).g0;
+    A.t_dc1 = (u64)(p.dims[0] - 3) * LCG_A;
+    A.t_dc2 = (u64)(p.dims[0] - 3) * LCG_BETA;
     A.m_R = c->m_R;
     A.m_tpr_log = c->m_tpr_log;
     A.cta_jump = c->l_cta_jump;
@@ -465,7 +482,8 @@ LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */
 }
 
 int sq_launch_update(sq_ctx *c, const LatticeArgs &A) {
-    if (A.m_on) CK(launch_lattice_march(A, c->p.math, c->ctas_per_slice, c->stream));
+    if (A.m_on == 2) CK(launch_lattice_tile(A, c->p.math, c->ctas_per_slice, c->stream));
+    else if (A.m_on) CK(launch_lattice_march(A, c->p.math, c->ctas_per_slice, c->stream));
     else CK(launch_lattice_step(A, c->p.real, c->p.math, c->ctas_per_slice, c->stream));
     return SQ_OK;
 }

@@ -110,12 +110,13 @@ struct LatticeArgs {
     double *partials;    // [nchains][nt][ctas_per_slice][2] (sum phi, sum phi^2), or null
     unsigned long long *nclamped;
     // ---- row-marching kernel (sq_march.cu), fp32 d = 3,4 with dims[0]/4 a power of two <= 256 ----
-    int m_on;                    // 1: launch lattice_march_kernel (gridDim.x = its own CTAs per slice)
+    int m_on;                    // 1: launch lattice_march_kernel (gridDim.x = its own CTAs per slice), 2: lattice_tile_kernel
     int m_R;                     // consecutive rows (x1) per thread; divides dims[1]
     int m_tpr_log;               // log2(threads per row) = log2(dims[0] / 4)
     const JumpEntry *cta_jump;   // [ctas per slice] jump over bx * rows_per_cta * L0 draws
     const JumpEntry *thr_jump;   // [256] jump over (ty * R * L0 + tx * 4) draws
     JumpEntry row_jump;          // jump over L0 draws (one row down at fixed x0)
+    u64 t_dck, t_dc1, t_dc2;     // tile kernel: per-row increments of the affine constant and of the two site constants
     // ---- multi-GPU slab ring (sq_slab.cu); slab_on == 0: everything below is unused ----------
     // direction 0 = the slice below local slice 0, 1 = the slice above local slice nt-1.
     int slab_on;
@@ -131,6 +132,10 @@ cudaError_t launch_lattice_step(const LatticeArgs &A, int real, int math, int ct
                                 cudaStream_t stream);
 cudaError_t preload_lattice_step(int real, int math, int ndim);
 cudaError_t launch_lattice_march(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream);
+// sq_tile.cu: the same tiles staged through shared memory by bulk asynchronous copies (LatticeArgs::m_on == 2)
+cudaError_t launch_lattice_tile(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream);
+bool tile_shape_ok(int L0, int L1, int tpr_log, int R);
+size_t tile_smem_bytes(int L0, int L1, int tpr_log, int R);
 
 struct FinalizeArgs {
     int nt, nchains, ctas_per_slice;

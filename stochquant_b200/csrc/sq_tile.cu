@@ -1,0 +1,518 @@
+// sq_tile.cu -- streaming Langevin step, fp32, d = 3 and 4: tile staging through shared memory by bulk
+// asynchronous copies, second design of the marching kernel (sq_march.cu).
+//
+// Same update as lattice_step_kernel / lattice_march_kernel (generalisation of tau_kernel.cl:64-173 defined in
+// DESIGN.md section 4 / oracle sqo_lattice_step) and the same integer stream.  The marching kernel was
+// instruction-bound (58 warp-instructions per site, profiles/r01_ring_c4s.txt): 18 of every strip's
+// instructions computed load addresses, 8 rolled the centre row through registers, and the two first-touch
+// FADD2s of the neighbour sum held a quarter of all stall samples.  Here
+//   * a CTA's tile -- rows_per_cta consecutive rows of one time slice -- is fetched ONCE into shared memory by
+//     cp.async.bulk copies (one per run of rows inside an (x2, t) plane, plus that run's two x1-halo rows, with
+//     the periodic wrap resolved by the copy's source address), completion on an mbarrier.  The centre strip,
+//     its x1+-1 neighbours and the two x0 neighbours then are LDS at base + immediate: no address arithmetic,
+//     no L1 round trip, no register rolling;
+//   * the four streams without reuse (t+-1, x2+-1) stay 128-bit global loads, issued at the top of a pass and
+//     consumed after the pass's noise phase: the draws and the Box-Muller arithmetic (2/3 of the instructions,
+//     no field data) run while they are in flight.  Their addresses are per-thread 64-bit bases + an immediate
+//     (the row stride is a template parameter for rows of 32 / 64 / 256 sites);
+//   * the LCG is walked in its t2 form (see sq_rowres.cu): two independent 48-bit multiply-adds per site.
+// CTA -> tile mapping, jump tables, per-CTA observable partials, clamp slots, replay entries (REBASE), L2
+// chunking and the slab ring's halo protocol are those of the marching kernel, so the host side is shared.
+#include "sq_strip_slow.cuh"
+
+namespace sq {
+
+namespace {
+
+constexpr unsigned ALPHA_LO32T = (unsigned)LCG_ALPHA, ALPHA_HI32T = (unsigned)(LCG_ALPHA >> 32);
+
+__device__ __forceinline__ void mad48t(unsigned xl, unsigned xh, unsigned ml, unsigned mh, u64 c, unsigned &rl, unsigned &rh) {
+    u64 p;
+    unsigned ph, t;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(xl), "r"(ml), "l"(c));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(rl), "=r"(ph) : "l"(p));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(xl), "r"(mh), "r"(ph));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(rh) : "r"(xh), "r"(ml), "r"(t));
+}
+__device__ __forceinline__ ulonglong2 lds128(unsigned a) {
+    ulonglong2 v;
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ ulonglong2 ldg128(const char *p) {
+    ulonglong2 v;
+    asm volatile("ld.global.v2.b64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void tile_mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tile_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA engine, no tensor map: a linear run of bytes); bytes % 16 == 0, both sides 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tile_mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+}  // namespace
+
+// L0T: row length known at compile time (0: runtime) -- the byte stride between a thread's passes becomes an immediate
+// REBASE: the step has replay entries (the common, event-free instance carries none of that code)
+template <int MATH, int NDIM, int POT, int L0T, bool REBASE>
+#ifndef TILE_MINB
+#define TILE_MINB 3
+#endif
+__global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kernel(const LatticeArgs A) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ int s_skip;
+    // an earlier launch flagged an event: this one will be replayed.  ONE thread decides for the CTA -- the word may rise
+    // between two threads' reads, and a CTA that has lost the warp which issues its copies would wait for them forever.
+    if (threadIdx.x == 0) s_skip = *((volatile const u64 *)A.event_key) != NO_EVENT;
+    const int chain = blockIdx.z;
+    int tl;
+    unsigned bx;
+    cta_slice_position(A, tl, bx);
+    const bool edge_lo = A.slab_on && tl == 0, edge_hi = A.slab_on && tl == A.nt - 1;
+    // ---- geometry: thread (tx, ty) owns strip position x0 = 4 tx of rows r_start .. r_start + R - 1 ------------
+    const unsigned L0 = L0T ? (unsigned)L0T : (unsigned)A.dim[0], L1 = (unsigned)A.dim[1];
+    const unsigned L2 = (NDIM >= 4) ? (unsigned)A.dim[2] : 1u;
+    const unsigned ROWB = L0 * 4u;  // bytes per row
+    const unsigned tx = threadIdx.x & ((1u << A.m_tpr_log) - 1u), ty = threadIdx.x >> A.m_tpr_log;
+    const unsigned R = (unsigned)A.m_R;
+    const unsigned rows_per_cta = (256u >> A.m_tpr_log) * R;
+    const unsigned tile_row0 = bx * rows_per_cta, r_start = tile_row0 + ty * R;
+    const long long vs = A.vslice;
+    const float *in = (const float *)A.in + (long long)chain * A.chain_stride;
+    const float *cur = in + (long long)tl * vs;
+
+    // ---- stage the tile: segments = runs of rows inside one plane, each stored as [halo_lo | rows | halo_hi] ---
+    const unsigned seg_rows = rows_per_cta < L1 ? rows_per_cta : L1, nseg = rows_per_cta / seg_rows;
+    const unsigned seg_bytes = (seg_rows + 2u) * ROWB;
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(tile_smem);
+    const unsigned bar = smem0, data0 = smem0 + 128u;
+    if (threadIdx.x == 0) tile_mbar_init(bar, 1);
+    if (edge_lo | edge_hi) {  // slab ring: the neighbour's boundary slice of this step's input must have landed
+        if (threadIdx.x == 0) {
+            if (edge_lo) slab_wait(A.wait_flag[0], A.wait_tag, A.slab_error);
+            if (edge_hi) slab_wait(A.wait_flag[1], A.wait_tag, A.slab_error);
+        }
+    }
+    __syncthreads();
+    if (s_skip) return;
+    if (threadIdx.x < 32) {
+        if (threadIdx.x == 0) tile_expect_tx(bar, nseg * seg_bytes);
+        __syncwarp();
+        for (unsigned c = threadIdx.x; c < 3u * nseg; c += 32u) {
+            const unsigned sg = c / 3u, part = c - 3u * sg;            // 0 rows, 1 halo below, 2 halo above
+            const unsigned row0 = tile_row0 + sg * seg_rows;            // first row of the run (row index inside the slice)
+            const unsigned x1a = row0 % L1, prow0 = row0 - x1a;         // its x1, first row of its plane
+            unsigned src_row, dst_off, bytes;
+            if (part == 0) { src_row = row0; dst_off = ROWB; bytes = seg_rows * ROWB; }
+            else if (part == 1) { src_row = (x1a == 0) ? prow0 + L1 - 1u : row0 - 1u; dst_off = 0; bytes = ROWB; }
+            else { src_row = (x1a + seg_rows == L1) ? prow0 : row0 + seg_rows; dst_off = (seg_rows + 1u) * ROWB; bytes = ROWB; }
+            bulk_g2s(data0 + sg * seg_bytes + dst_off, cur + (size_t)src_row * L0, bytes, bar);
+        }
+    }
+
+    unsigned x1s = r_start, x2 = 0;
+    if (NDIM >= 4) {
+        x2 = r_start / L1;
+        x1s = r_start - x2 * L1;
+    }
+    (void)x1s;
+    const unsigned x0 = tx * 4u;
+    const float *tm = (tl > 0) ? cur - vs : (A.wrap_time ? in + (long long)(A.nt - 1) * vs : (const float *)A.ghost_lo);
+    const float *tp = (tl < A.nt - 1) ? cur + vs : (A.wrap_time ? in : (const float *)A.ghost_hi);
+    float *dst = (float *)A.out + (long long)chain * A.chain_stride + (long long)tl * vs;
+    const bool push_lo = edge_lo && A.push_tag, push_hi = edge_hi && A.push_tag;
+    const unsigned plane = L0 * L1;
+    const unsigned o0 = r_start * L0 + x0;  // offset of the thread's first strip inside the slice (reals)
+    unsigned o = o0;                        // (REBASE) offset of the strip in hand
+    // per-thread stream bases (bytes); pass k adds k * ROWB
+    const char *p_tp = (const char *)(tp + o), *p_tm = (const char *)(tm + o);
+    const char *p_u2 = nullptr, *p_d2 = nullptr;
+    if (NDIM >= 4) {
+        p_u2 = (const char *)(cur + o) + (long long)((x2 + 1 == L2) ? -(long long)(L2 - 1) * plane : (long long)plane) * 4;
+        p_d2 = (const char *)(cur + o) + (long long)((x2 == 0) ? (long long)(L2 - 1) * plane : -(long long)plane) * 4;
+    }
+    char *p_dst = (char *)(dst + o);
+    // shared-memory addresses of the thread's first strip and its x0 neighbours
+    const unsigned rt = ty * R;  // row inside the tile
+    const unsigned sg_t = rt / seg_rows;
+    const unsigned s_row = data0 + sg_t * seg_bytes + (1u + rt - sg_t * seg_rows) * ROWB;
+    unsigned s_c = s_row + x0 * 4u;
+    unsigned s_left = s_row + ((x0 == 0) ? (L0 - 1u) * 4u : x0 * 4u - 4u);
+    unsigned s_right = s_row + ((x0 + 4 == L0) ? 0u : x0 * 4u + 16u);
+
+    // ---- chain state: T = seed before the thread's first draw + 2^31, per-row affine advance ------------------
+    const u64 gslice = (u64)(A.slab_t0 + tl) * (u64)vs;
+    const u64 S = A.seed_in[chain];
+    unsigned cnt_prev = 0, nxt32 = 0x7FFFFFFFu;
+    u64 S_eff = S;
+    if (REBASE) {
+        const Rebased rb = rebase_eval(A.rebase, A.n_rebase, chain, S, gslice + o, gslice, (unsigned)vs);
+        S_eff = rb.S_eff;
+        cnt_prev = rb.cnt;
+        nxt32 = rb.slow ? o : rb.nxt32;  // an entry inside the first strip: take the rare path at k == 0
+    }
+    // three precomputed jumps from gid 0: slice start, CTA's first row, this thread's first strip
+    unsigned Tl, Th;
+    {
+        const u64 g_cta = gslice + (u64)bx * rows_per_cta * L0;
+        const u64 s_sl = lcg_apply(A.slice_jump[tl], S_eff, 0) & LCG_MASK;
+        const u64 s_cta = lcg_apply(A.cta_jump[bx], s_sl, gslice) & LCG_MASK;
+        const u64 s = lcg_apply(A.thr_jump[threadIdx.x], s_cta, g_cta) & LCG_MASK;
+        const u64 T = s + TWO31;
+        Tl = (unsigned)T;
+        Th = (unsigned)(T >> 32);
+    }
+    const unsigned aDl = (unsigned)A.row_jump.a, aDh = (unsigned)(A.row_jump.a >> 32);
+    // T(next row) = alpha^L0 T + ck ; ck itself is a running sum
+    u64 ck = (LCG_BETA * (gslice + o) + LCG_GAMMA) * A.row_jump.g0 + A.row_jump.bg1 - A.row_jump.a * TWO31 + TWO31;
+    // site constants of the strip's first site: t1 = A T + c1, T' = A^2 T + c2 ; +A / +(A^2+A) per site
+    u64 c1 = site_const(gslice + o) - LCG_A * TWO31;
+    u64 c2 = (LCG_A + 1) * site_const(gslice + o) - LCG_ALPHA * TWO31;
+    // (the per-row increments A.t_dck, A.t_dc1 = (L0 - 3) A, A.t_dc2 = (L0 - 3)(A^2 + A) are kernel parameters: constant-bank
+    // operands of the adds, not registers)
+
+    // ---- constants as fp32 pairs -------------------------------------------------------------------------
+    const float c_lap = (float)A.c_lap, c_dt = (float)A.c_dt;
+    const float m2 = (float)(A.m2_chain ? A.m2_chain[chain] : A.m2);
+    const float lam = (float)(A.lam_chain ? A.lam_chain[chain] : A.lam);
+    const pair_t K_m2d = pk(-(float)(2 * NDIM), -(float)(2 * NDIM)), K_clap = pk(c_lap, c_lap);
+    const pair_t K_m2cdt = pk(-2.0f * c_dt, -2.0f * c_dt), K_mcdt = pk(-c_dt, -c_dt);
+    const pair_t K_lam = pk(lam, lam), K_m2 = pk(m2, m2), K_m1 = pk(-1.0f, -1.0f);
+    const pair_t K_2m32 = pk(2.3283064365386963e-10f, 2.3283064365386963e-10f), K_k2 = pk(A.k2_f, A.k2_f);
+    const float kth = (float)(2.0 * 3.1415 / 4294967296.0);  // theta - pi = 2*3.1415 v2 - pi, v2 = (float)u2 * 2^-32
+    const pair_t K_th = pk(kth, kth), K_mpi = pk(-3.14159265358979f, -3.14159265358979f);
+    (void)K_m2cdt; (void)K_mcdt; (void)K_lam; (void)K_m2; (void)K_2m32; (void)K_k2; (void)K_th; (void)K_mpi;
+
+    pair_t ACC1 = 0, ACC2 = 0;  // (+0.0f, +0.0f)
+    unsigned nclamp = 0;
+
+    // ---- one pass = one strip of 4 sites; `kb` = byte offset of the pass inside the thread's streams --------
+    auto pass = [&](const unsigned kb, const unsigned k) {
+        // t+-1 and x2+-1 have no reuse: straight from global memory, requested now, used after the noise phase
+        ulonglong2 U2, D2;
+        if (NDIM >= 4) {
+            U2 = ldg128(p_u2 + kb);
+            D2 = ldg128(p_d2 + kb);
+        }
+        const ulonglong2 TP = ldg128(p_tp + kb), TM = ldg128(p_tm + kb);
+
+        // ---- noise phase: 4 draws in t2 form, Box-Muller ------------------------------------------------
+        const unsigned T0l = Tl, T0h = Th;
+        unsigned tl_ = Tl, th_ = Th, um = 0xFFFFFFFFu;
+        pair_t NZ[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            unsigned u1a, u2a, u1b, u2b, al, ah, bl, bh;
+            mad48t(tl_, th_, A_LO, A_HI, c1, al, ah);
+            mad48t(tl_, th_, ALPHA_LO32T, ALPHA_HI32T, c2, bl, bh);
+            u1a = __funnelshift_r(al, ah, 16);
+            u2a = __funnelshift_r(bl, bh, 16);
+            c1 += LCG_A;
+            c2 += LCG_BETA;
+            mad48t(bl, bh, A_LO, A_HI, c1, al, ah);
+            mad48t(bl, bh, ALPHA_LO32T, ALPHA_HI32T, c2, tl_, th_);
+            u1b = __funnelshift_r(al, ah, 16);
+            u2b = __funnelshift_r(tl_, th_, 16);
+            if (q == 0) {
+                c1 += LCG_A;
+                c2 += LCG_BETA;
+            } else {  // on to the first site of the next row
+                c1 += A.t_dc1;
+                c2 += A.t_dc2;
+            }
+            um = min(min(um, u1a), u2a);  // u1 == 0 (retry) or u2 < 2^15 (`seed+=`) => um < 2^15
+            um = min(min(um, u1b), u2b);
+            if (MATH == 1) {
+                float l1a, l1b, ta, tb, tha, thb;
+                upk(mul2(pk(__uint2float_rn(u1a), __uint2float_rn(u1b)), K_2m32), l1a, l1b);
+                upk(mul2(pk(lg2_approx(l1a), lg2_approx(l1b)), K_k2), ta, tb);
+                upk(fma2(pk(__uint2float_rn(u2a), __uint2float_rn(u2b)), K_th, K_mpi), tha, thb);
+                NZ[q] = mul2(pk(__cosf(tha), __cosf(thb)), pk(sqrt_approx(fabsf(ta)), sqrt_approx(fabsf(tb))));
+            } else {
+                const float da = (float)__dmul_rn(A.nscale, noise_accurate((u64)u1a << 16, (u64)u2a << 16));
+                const float db = (float)__dmul_rn(A.nscale, noise_accurate((u64)u1b << 16, (u64)u2b << 16));
+                NZ[q] = pk(-da, -db);
+            }
+        }
+        {   // next row: same x0, L0 draws further
+            mad48t(T0l, T0h, aDl, aDh, ck, Tl, Th);
+            ck += A.t_dck;
+        }
+
+        // ---- stencil phase ------------------------------------------------------------------------------------
+        const ulonglong2 C = lds128(s_c + kb), U1 = lds128(s_c + kb + ROWB), D1 = lds128(s_c + kb - ROWB);
+        const float left = lds32(s_left + kb), right = lds32(s_right + kb);
+        float c0, c1f, c2f, c3;
+        upk(C.x, c0, c1f);
+        upk(C.y, c2f, c3);
+        pair_t S01 = pk(__fadd_rn(c1f, left), __fadd_rn(c2f, c0));  // phi(+0) + phi(-0)
+        pair_t S23 = pk(__fadd_rn(c3, c1f), __fadd_rn(right, c2f));
+        S01 = add2(S01, U1.x);
+        S23 = add2(S23, U1.y);
+        S01 = add2(S01, D1.x);
+        S23 = add2(S23, D1.y);
+        if (NDIM >= 4) {
+            S01 = add2(S01, U2.x);
+            S23 = add2(S23, U2.y);
+            S01 = add2(S01, D2.x);
+            S23 = add2(S23, D2.y);
+        }
+        S01 = add2(S01, TP.x);
+        S23 = add2(S23, TP.y);
+        S01 = add2(S01, TM.x);
+        S23 = add2(S23, TM.y);
+        pair_t V01 = fma2(K_clap, fma2(K_m2d, C.x, S01), C.x);
+        pair_t V23 = fma2(K_clap, fma2(K_m2d, C.y, S23), C.y);
+        if (POT == 4) {
+            V01 = fma2(K_mcdt, mul2(C.x, fma2(K_lam, mul2(C.x, C.x), K_m2)), V01);
+            V23 = fma2(K_mcdt, mul2(C.y, fma2(K_lam, mul2(C.y, C.y), K_m2)), V23);
+        } else {
+            V01 = fma2(K_m2cdt, C.x, V01);  // (-c_dt)(2 phi) == (-2 c_dt) phi exactly
+            V23 = fma2(K_m2cdt, C.y, V23);
+        }
+        V01 = fma2(K_m1, NZ[0], V01);  // v + dw, one rounding
+        V23 = fma2(K_m1, NZ[1], V23);
+        // clamp (tau_kernel.cl:122-132): values at or beyond +-1000 leave through one test per strip
+        float v0, v1, v2, v3;
+        upk(V01, v0, v1);
+        upk(V23, v2, v3);
+        const float amax = fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3)));
+        if (__builtin_expect(!(amax < 1000.0f) | (um < 32768u), 0)) {  // one test per strip for both rare cases
+            bool replayed = false;  // an event in this strip: the launch is redone, its clamp hits are not counted
+            if (um < 32768u) {
+                const u64 z0 = ((((u64)T0h << 32) | T0l) - TWO31) & LCG_MASK;
+                replayed = strip_events_cold(A.event_key, A.step_index, chain, z0, (u64)(A.slab_t0 + tl) * (u64)A.vslice + o0 + k * L0, 4);
+            }
+            const Clamped cl = clamp_cold(v0, v1, v2, v3);
+            V01 = pk(cl.v[0], cl.v[1]);
+            V23 = pk(cl.v[2], cl.v[3]);
+            if (!replayed) nclamp += cl.n;
+        }
+        // ---- observables of the pre-update field, store ------------------------------------------------------
+        ACC1 = add2(ACC1, C.x);
+        ACC1 = add2(ACC1, C.y);
+        ACC2 = fma2(C.x, C.x, ACC2);
+        ACC2 = fma2(C.y, C.y, ACC2);
+        *reinterpret_cast<ulonglong2 *>(p_dst + kb) = make_ulonglong2(V01, V23);
+        if (__builtin_expect(push_lo | push_hi, 0)) {  // CTA-uniform: boundary slices of a slab ring only
+            const size_t oo = (size_t)(o0 + k * L0) * 4u;
+            if (push_lo) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[0] + oo) = make_ulonglong2(V01, V23);
+            if (push_hi) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[1] + oo) = make_ulonglong2(V01, V23);
+        }
+    };
+
+    // ---- a whole strip on the rare path (a replay entry's first site or its overridden site lies inside it) ----
+    auto slow_strip = [&](const unsigned k) {
+        const unsigned x1 = ((NDIM >= 4) ? (r_start - x2 * L1) : r_start) + k;
+        const u64 gsl = (u64)(A.slab_t0 + tl) * (u64)A.vslice;
+        const u64 g0 = gsl + o;
+        const Rebased rb = rebase_eval(A.rebase, A.n_rebase, chain, A.seed_in[chain], g0, gsl, (unsigned)A.vslice);
+        nxt32 = rb.nxt32;
+        if (rb.cnt != cnt_prev) {  // new base: the thread's first strip under the new start seed, k rows down
+            cnt_prev = rb.cnt;
+            const u64 gc = gsl + (u64)bx * rows_per_cta * L0;
+            const u64 s_sl = lcg_apply(A.slice_jump[tl], rb.S_eff, 0) & LCG_MASK;
+            const u64 s_cta = lcg_apply(A.cta_jump[bx], s_sl, gsl) & LCG_MASK;
+            u64 t = (lcg_apply(A.thr_jump[threadIdx.x], s_cta, gc) & LCG_MASK) + TWO31;
+            u64 cj = (LCG_BETA * (g0 - (u64)k * L0) + LCG_GAMMA) * A.row_jump.g0 + A.row_jump.bg1 - A.row_jump.a * TWO31 + TWO31;
+            for (unsigned j = 0; j < k; ++j) {
+                t = A.row_jump.a * t + cj;
+                cj += A.t_dck;
+            }
+            Tl = (unsigned)t;
+            Th = (unsigned)(t >> 32);
+        }
+        if (!rb.slow) return false;
+        // the whole strip out of line; the row recurrence is void behind an entry (re-evaluated at the next strip)
+        const unsigned row_wrap = (L1 - 1) * L0;
+        SlowIn I;
+        I.cur = cur; I.tm = tm; I.tp = tp; I.dst = dst;
+        I.push0 = push_lo ? (float *)A.push_ghost[0] : nullptr;
+        I.push1 = push_hi ? (float *)A.push_ghost[1] : nullptr;
+        I.o = o;
+        I.o_up1 = o + ((x1 + 1 == L1) ? 0u - row_wrap : L0);
+        I.o_dn1 = o + ((x1 == 0) ? row_wrap : 0u - L0);
+        I.o_up2 = (NDIM >= 4) ? o + ((x2 + 1 == L2) ? 0u - (L2 - 1) * plane : plane) : 0u;
+        I.o_dn2 = (NDIM >= 4) ? o + ((x2 == 0) ? (L2 - 1) * plane : 0u - plane) : 0u;
+        I.o_left = o + ((x0 == 0) ? L0 - 1u : 0u - 1u);
+        I.o_right = o + ((x0 + 4 == L0) ? 4u - L0 : 4u);
+        I.s = ((((u64)Th << 32) | Tl) - TWO31) & LCG_MASK;
+        I.g0 = g0;
+        I.chain = chain; I.step_index = A.step_index; I.n_rebase = A.n_rebase;
+        I.rebase = A.rebase; I.event_key = A.event_key;
+        I.c_lap = c_lap; I.c_dt = c_dt; I.m2 = m2; I.lam = lam; I.k2 = A.k2_f; I.nscale = A.nscale;
+        const SlowOut so = strip_slow<MATH, NDIM, POT>(I);
+        ACC1 = add2(ACC1, pk(so.a1, 0.f));
+        ACC2 = add2(ACC2, pk(so.a2, 0.f));
+        nclamp += so.nclamp;
+        nxt32 = o + L0;  // re-evaluate at the next strip (new base)
+        ck += A.t_dck;
+        c1 += (u64)L0 * LCG_A;
+        c2 += (u64)L0 * LCG_BETA;
+        return true;
+    };
+
+    tile_mbar_wait(bar, 0);  // the tile has landed (other CTAs of the SM computed meanwhile)
+    // ---- the thread's R strips: U passes per trip (pass offsets are immediates), then the stream bases move on --------
+    // (R is a multiple of 4 -- tile_shape_ok -- so the event-free instance needs no tail test)
+    constexpr unsigned U = REBASE ? 1u : 4u;
+    for (unsigned k0 = 0; k0 < R; k0 += U) {
+#pragma unroll
+        for (unsigned u = 0; u < U; ++u) {
+            // replay entries: a thread visits its strips in increasing gid, so it only watches the distance to the NEXT
+            // entry (32-bit, relative to the slice); reaching one re-evaluates the base with the full 64-bit logic
+            bool done = false;
+            if (REBASE) {
+                o = o0 + (k0 + u) * L0;
+                if (__builtin_expect((int)(nxt32 - o) <= 4, 0)) done = slow_strip(k0 + u);
+            }
+            if (!done) pass(u * ROWB, k0 + u);
+        }
+        p_tp += U * ROWB;
+        p_tm += U * ROWB;
+        if (NDIM >= 4) {
+            p_u2 += U * ROWB;
+            p_d2 += U * ROWB;
+        }
+        p_dst += U * ROWB;
+        // (opaque: otherwise the four streams are rewritten as ONE running offset plus four bases, and every load pays a
+        // 64-bit add again instead of using base + immediate)
+        asm volatile("" : "+l"(p_tp), "+l"(p_tm), "+l"(p_u2), "+l"(p_d2), "+l"(p_dst));
+        s_c += U * ROWB;
+        s_left += U * ROWB;
+        s_right += U * ROWB;
+    }
+
+    if (push_lo || push_hi) {  // last CTA of the slice: everything is out, raise the neighbour's flag
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (push_lo && atomicAdd(A.push_count + 0, 1u) == gridDim.x - 1) {
+                A.push_count[0] = 0;
+                __threadfence_system();
+                st_release_sys_u32(A.push_flag[0], A.push_tag);
+            }
+            if (push_hi && atomicAdd(A.push_count + 1, 1u) == gridDim.x - 1) {
+                A.push_count[1] = 0;
+                __threadfence_system();
+                st_release_sys_u32(A.push_flag[1], A.push_tag);
+            }
+        }
+    }
+
+    // ---- the omega work-item's draw (gid = V) and the step's final seed -------------------------------------
+    if (bx == 0 && tl == 0 && threadIdx.x == 0) {
+        const u64 Vg = (u64)A.V;
+        u64 sv, t1, t2;
+        bool overridden = false;
+        u64 next = 0;
+        if (REBASE) {
+            u64 bg, bs;
+            rebase_lookup(A, chain, S, Vg, bg, bs);
+            sv = lcg_seed_at(bs, bg, Vg - bg, A.jump);
+            for (int j = 0; j < A.n_rebase; ++j)
+                if (A.rebase[j].chain == chain && A.rebase[j].ov_gid == Vg) {
+                    overridden = true;
+                    next = A.rebase[j].seed;  // entry with gid_start == V+1
+                }
+        } else {
+            sv = lcg_apply(A.vol_jump, S, 0) & LCG_MASK;
+        }
+        lcg_draw(sv, Vg, t1, t2);
+        if (!overridden) {
+            if (lcg_event(sv & LCG_MASK, t1, t2))
+                atomicMin((unsigned long long *)A.event_key, event_key(A.step_index, chain, Vg));
+            next = lcg_next_seed(t2);
+        }
+        A.seed_out[chain] = next;
+    }
+
+    // ---- per-CTA observable partial ---------------------------------------------------------------------------
+    if (A.partials) {
+        __shared__ double red[2][8];
+        float a1l, a1h, a2l, a2h;
+        upk(ACC1, a1l, a1h);
+        upk(ACC2, a2l, a2h);
+        double a1 = warp_sum((double)a1l + (double)a1h), a2 = warp_sum((double)a2l + (double)a2h);
+        const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+        if (l == 0) { red[0][w] = a1; red[1][w] = a2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s1 = 0, s2 = 0;
+            for (int q = 0; q < 8; ++q) { s1 += red[0][q]; s2 += red[1][q]; }
+            double *p = A.partials + (((long long)chain * A.nt + tl) * gridDim.x + bx) * 2;
+            p[0] = s1;
+            p[1] = s2;
+        }
+    }
+    if (nclamp) atomicAdd(A.nclamped, (unsigned long long)nclamp);
+}
+
+// shared memory a CTA needs: one mbarrier line + [halo | rows | halo] per run of rows inside a plane
+size_t tile_smem_bytes(int L0, int L1, int tpr_log, int R) {
+    const unsigned rows_per_cta = (256u >> tpr_log) * (unsigned)R;
+    const unsigned seg_rows = rows_per_cta < (unsigned)L1 ? rows_per_cta : (unsigned)L1, nseg = rows_per_cta / seg_rows;
+    return 128 + (size_t)nseg * (seg_rows + 2u) * (size_t)L0 * 4u;
+}
+// the tile must be a whole number of planes or divide one (runs of rows never straddle a plane edge)
+bool tile_shape_ok(int L0, int L1, int tpr_log, int R) {
+    const unsigned rows_per_cta = (256u >> tpr_log) * (unsigned)R;
+    if (L1 % R != 0 || R % 4 != 0) return false;
+    if (!(rows_per_cta % (unsigned)L1 == 0 || (unsigned)L1 % rows_per_cta == 0)) return false;
+    return tile_smem_bytes(L0, L1, tpr_log, R) <= 72 * 1024;  // three CTAs per SM (the register budget allows no more)
+}
+
+template <int MATH, int NDIM, int POT, int L0T>
+static cudaError_t tile_go(const LatticeArgs &A, dim3 grid, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024) {  // (idempotent; the attribute is per function)
+        cudaError_t e = cudaFuncSetAttribute(lattice_tile_kernel<MATH, NDIM, POT, L0T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(lattice_tile_kernel<MATH, NDIM, POT, L0T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    if (A.n_rebase > 0) lattice_tile_kernel<MATH, NDIM, POT, L0T, true><<<grid, 256, smem, st>>>(A);
+    else lattice_tile_kernel<MATH, NDIM, POT, L0T, false><<<grid, 256, smem, st>>>(A);
+    return cudaGetLastError();
+}
+template <int MATH, int NDIM, int POT>
+static cudaError_t tile_l0(const LatticeArgs &A, dim3 grid, size_t smem, cudaStream_t st) {
+    switch (A.dim[0]) {
+        case 32: return tile_go<MATH, NDIM, POT, 32>(A, grid, smem, st);
+        case 64: return tile_go<MATH, NDIM, POT, 64>(A, grid, smem, st);
+        case 256: return tile_go<MATH, NDIM, POT, 256>(A, grid, smem, st);
+    }
+    return tile_go<MATH, NDIM, POT, 0>(A, grid, smem, st);
+}
+template <int MATH, int NDIM>
+static cudaError_t tile_pot(const LatticeArgs &A, dim3 grid, size_t smem, cudaStream_t st) {
+    return A.pot == 4 ? tile_l0<MATH, NDIM, 4>(A, grid, smem, st) : tile_l0<MATH, NDIM, 0>(A, grid, smem, st);
+}
+
+cudaError_t launch_lattice_tile(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream) {
+    dim3 grid((unsigned)ctas_per_slice, (unsigned)A.nt, (unsigned)A.nchains);
+    const size_t smem = tile_smem_bytes((int)A.dim[0], (int)A.dim[1], A.m_tpr_log, A.m_R);
+    if (A.ndim == 3) return math ? tile_pot<1, 3>(A, grid, smem, stream) : tile_pot<0, 3>(A, grid, smem, stream);
+    if (A.ndim == 4) return math ? tile_pot<1, 4>(A, grid, smem, stream) : tile_pot<0, 4>(A, grid, smem, stream);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace sq
