@@ -52,9 +52,24 @@ int main(int argc, char **argv)
     unsigned long rand1 = 0;
     int rec_sim_length = 0;
     th_initial_state(n, a.deltat, a.deltatau, cold, f, &omega, &rand1);
-    if (!cold && th_read_start_file(a.start_file, n, a.deltatau, xavg, xx0, x, f, &rec_sim_length, &dtau)) {
+    /* TAUHOST_EXT_TRAILER=1 (not a reference feature): write the extended trailer behind the end
+     * file's three trailer lines and honour one found in the start file -- a bit-exact resume.  Unset: the
+     * reference's behaviour to the letter (restart re-randomises omega and the seed, `N` double-counts). */
+    const char *ext_env = getenv("TAUHOST_EXT_TRAILER");
+    const int use_ext = ext_env && atoi(ext_env) == 1;
+    th_ext ext;
+    int has_ext = 0;
+    memset(&ext, 0, sizeof ext);
+    if (!cold && th_read_start_file_ext(a.start_file, n, a.deltatau, xavg, xx0, x, f, &rec_sim_length, &dtau, &ext, &has_ext)) {
         fprintf(stderr, "Failed to read Input.\n");
         return 1;
+    }
+    has_ext = has_ext && use_ext;
+    if (has_ext) { /* continue as if the run had never stopped */
+        omega = ext.omega;
+        rand1 = (unsigned long)ext.seed;
+        dtau = ext.dtau;
+        rec_sim_length = 0;
     }
 
     const int ndev = sq_device_count();
@@ -89,8 +104,15 @@ int main(int argc, char **argv)
      * batches with no host round trip in between (sq_frames); the host formats the lines afterwards.
      * Line j shows the xavg of the last accepted frame before j and the step size frame j ran with,
      * exactly what the reference prints between its clFinish and its read-backs (:483-501). */
-    int64_t runs = rec_sim_length;
-    int stab_cnt = 0;
+    int64_t runs = has_ext ? (int64_t)ext.runs : rec_sim_length;
+    int stab_cnt = has_ext ? ext.stab_cnt : 0;
+    if (has_ext) {
+        sq_compat_state st;
+        memset(&st, 0, sizeof st);
+        st.struct_size = sizeof st;
+        st.seed = ext.seed; st.lrgEl = ext.lrgEl; st.lrgVl = ext.lrgVl; st.omega = ext.omega; st.newf_lrgEl = ext.newf_lrgEl;
+        if ((rc = sq_compat_set_state(ctx, &st)) != SQ_OK) return fail_sq("sq_compat_set_state", rc);
+    }
     if ((rc = sq_controller_set(ctx, dtau, runs, stab_cnt)) != SQ_OK) return fail_sq("sq_controller_set", rc);
     sq_frame_rec recs[SQ_FRAMES_MAX];
     double *xlog = (double *)malloc(sizeof(double) * (size_t)SQ_FRAMES_MAX * (size_t)n);
@@ -114,7 +136,18 @@ int main(int argc, char **argv)
 
     int status = 0;
     if (strcmp(a.end_file, "0") != 0) {
-        if (th_write_end_file(a.end_file, n, a.end_accuracy, xavg, xx0, x, f, omega, (int)runs + rec_sim_length, dtau)) {
+        th_ext out;
+        memset(&out, 0, sizeof out);
+        if (use_ext) {
+            sq_compat_state st;
+            memset(&st, 0, sizeof st);
+            st.struct_size = sizeof st;
+            if ((rc = sq_compat_get_state(ctx, &st)) != SQ_OK) return fail_sq("sq_compat_get_state", rc);
+            out.seed = st.seed; out.lrgEl = st.lrgEl; out.lrgVl = st.lrgVl; out.omega = st.omega; out.newf_lrgEl = st.newf_lrgEl;
+            out.dtau = dtau; out.stab_cnt = stab_cnt; out.runs = (long long)runs;
+        }
+        if (th_write_end_file_ext(a.end_file, n, a.end_accuracy, xavg, xx0, x, f, omega, (int)runs + rec_sim_length, dtau,
+                                  use_ext ? &out : NULL)) {
             fprintf(stderr, "Failed to write to Output.\n");
             status = 1;
         }

@@ -99,6 +99,12 @@ int th_print_frame(FILE *out, int n, const double *xavg, double dtau, int frame,
 int th_write_end_file(const char *path, int n, int width, const double *xavg, const double *xx0,
                       const double *x, const double *f, double omega, int runs_field, double dtau)
 {
+    return th_write_end_file_ext(path, n, width, xavg, xx0, x, f, omega, runs_field, dtau, NULL);
+}
+
+int th_write_end_file_ext(const char *path, int n, int width, const double *xavg, const double *xx0,
+                          const double *x, const double *f, double omega, int runs_field, double dtau, const th_ext *ext)
+{
     FILE *fp = fopen(path, "w");
     if (!fp) return 1;
     for (int i = 0; i < n; ++i)
@@ -106,6 +112,17 @@ int th_write_end_file(const char *path, int n, int width, const double *xavg, co
     fprintf(fp, "% -*a|omega\n", width, omega);
     fprintf(fp, "%*d|N\n", width, runs_field);
     fprintf(fp, "% -*e|deltaTau\n", width, dtau);
+    if (ext) {
+        fprintf(fp, "1|sqext\n");
+        fprintf(fp, "%llu|rand1\n", ext->seed);
+        fprintf(fp, "%d|lrgEl\n", ext->lrgEl);
+        fprintf(fp, "%a|lrgVl\n", ext->lrgVl);
+        fprintf(fp, "%a|omega\n", ext->omega);
+        fprintf(fp, "%a|newf_lrgEl\n", ext->newf_lrgEl);
+        fprintf(fp, "%a|deltaTau\n", ext->dtau);
+        fprintf(fp, "%d|stabCnt\n", ext->stab_cnt);
+        fprintf(fp, "%lld|runs\n", ext->runs);
+    }
     fclose(fp);
     return 0;
 }
@@ -127,6 +144,14 @@ static char *next_field(char **cursor)
 int th_read_start_file(const char *path, int n, double deltatau, double *xavg, double *xx0,
                        double *x, double *f, int *rec_sim_length, double *dtau)
 {
+    return th_read_start_file_ext(path, n, deltatau, xavg, xx0, x, f, rec_sim_length, dtau, NULL, NULL);
+}
+
+int th_read_start_file_ext(const char *path, int n, double deltatau, double *xavg, double *xx0,
+                           double *x, double *f, int *rec_sim_length, double *dtau, th_ext *ext, int *has_ext)
+{
+    int ext_lines = 0;
+    if (has_ext) *has_ext = 0;
     FILE *fp = fopen(path, "r");
     if (!fp) return 1;
     char *line = NULL;
@@ -151,9 +176,25 @@ int th_read_start_file(const char *path, int n, double deltatau, double *xavg, d
                 double d = atof(tok);
                 *dtau = d > deltatau ? deltatau : d;
             }
+        } else if (row > n + 2 && ext) { /* extended trailer: "value|name" lines behind the reference's three */
+            char *val = next_field(&cur), *name = next_field(&cur);
+            if (val && name) {
+                if (row == n + 3) { if (strcmp(name, "sqext") == 0 && atoi(val) == 1) ext_lines = 1; }
+                else if (ext_lines >= 1) {
+                    if (!strcmp(name, "rand1")) { ext->seed = strtoull(val, NULL, 10); ++ext_lines; }
+                    else if (!strcmp(name, "lrgEl")) { ext->lrgEl = atoi(val); ++ext_lines; }
+                    else if (!strcmp(name, "lrgVl")) { ext->lrgVl = strtod(val, NULL); ++ext_lines; }
+                    else if (!strcmp(name, "omega")) { ext->omega = strtod(val, NULL); ++ext_lines; }
+                    else if (!strcmp(name, "newf_lrgEl")) { ext->newf_lrgEl = strtod(val, NULL); ++ext_lines; }
+                    else if (!strcmp(name, "deltaTau")) { ext->dtau = strtod(val, NULL); ++ext_lines; }
+                    else if (!strcmp(name, "stabCnt")) { ext->stab_cnt = atoi(val); ++ext_lines; }
+                    else if (!strcmp(name, "runs")) { ext->runs = atoll(val); ++ext_lines; }
+                }
+            }
         } /* row == n: the omega line is ignored (tauhost.c:122-124) */
         ++row;
     }
+    if (has_ext && ext_lines == 9) *has_ext = 1;
     free(line);
     fclose(fp);
     return 0;

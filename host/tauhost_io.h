@@ -47,6 +47,26 @@ int th_write_end_file(const char *path, int n, int width, const double *xavg, co
 int th_read_start_file(const char *path, int n, double deltatau, double *xavg, double *xx0,
                        double *x, double *f, int *rec_sim_length, double *dtau);
 
+/* ---- extended trailer: what the reference's end file lacks for a bit-exact resume.
+ * Written BEHIND the reference's three trailer lines, one "value|name" line each, first line "1|sqext":
+ * the reference's reader (tauhost.c:116-168) acts on lines 0..N+2 only, so such a file still restarts the
+ * reference (which then re-randomises as it always does).  A restart that honours the trailer continues the
+ * run as if it had never stopped: same seed, lrgEl / lrgVl, omega, the stale newf[lrgEl], the step size to the
+ * last bit (the reference prints it with 7 digits), the controller's counter and the true tau-step count (the
+ * reference's `N` line double-counts across restarts, tauhost.c:477,577). */
+typedef struct th_ext {
+    unsigned long long seed;   /* device RNG seed `rand1` */
+    int lrgEl, stab_cnt;
+    long long runs;            /* tau-steps in the running means */
+    double lrgVl, omega, newf_lrgEl, dtau;
+} th_ext;
+/* th_write_end_file + the extended trailer (ext == NULL: exactly th_write_end_file) */
+int th_write_end_file_ext(const char *path, int n, int width, const double *xavg, const double *xx0,
+                          const double *x, const double *f, double omega, int runs_field, double dtau, const th_ext *ext);
+/* th_read_start_file; *has_ext = 1 and *ext filled when the file carries a complete extended trailer */
+int th_read_start_file_ext(const char *path, int n, double deltatau, double *xavg, double *xx0,
+                           double *x, double *f, int *rec_sim_length, double *dtau, th_ext *ext, int *has_ext);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SQ_API_VERSION 2
+#define SQ_API_VERSION 3
 
 /* error codes */
 #define SQ_OK 0
@@ -155,6 +155,22 @@ int sq_controller_get(sq_ctx *ctx, double *dtau, int64_t *runs, int *stab_cnt);
  * xavg (NULL to skip): [nframes][N], row k = xx0[i]-x[i]*x[mid] after frame k if it was stable
  * (tauhost.c:519-521), else untouched.  Synchronous. */
 int sq_frames(sq_ctx *ctx, int nframes, int nsteps, sq_frame_rec *recs, double *xavg);
+
+/* ---- exact resume (COMPAT1D) ----------------------------------------------
+ * The reference's end file (tauhost.c:562-581) does not hold everything a run needs to continue
+ * bit-exactly: the device seed `rand1`, lrgEl / lrgVl (which survive frames and rollbacks,
+ * tauhost.c:533-554), omega (written but ignored on read, :122-124) and the one stale value
+ * newf[lrgEl] the stability scan compares against after a rejected frame (tau_kernel.cl:135) are
+ * lost, so a restarted reference run re-randomises them.  These two entry points let the host carry
+ * them in an extended trailer (host/tauhost_io.h) behind the reference's three trailer lines. */
+typedef struct sq_compat_state {
+    uint32_t struct_size;
+    int32_t lrgEl;
+    uint64_t seed;
+    double lrgVl, omega, newf_lrgEl;
+} sq_compat_state;
+int sq_compat_get_state(sq_ctx *ctx, sq_compat_state *out);
+int sq_compat_set_state(sq_ctx *ctx, const sq_compat_state *in);
 
 /* ---- support ----------------------------------------------------------------- */
 const char *sq_strerror(int code);

@@ -602,8 +602,6 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     // single-chain and takes them by value: keep both in sync through sq_set_chain (host mirror)
     if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     A.rows_max = c->res_rows;
-    static const int dbg = getenv("SQ_ROWRES_DEBUG") ? atoi(getenv("SQ_ROWRES_DEBUG")) : 0;  // timing experiments (wrong results)
-    A.debug = dbg;
     A.nclamp_slots = c->r_nclamp_slots;
     static const int strip_w = getenv("SQ_RESIDENT_STRIP") ? atoi(getenv("SQ_RESIDENT_STRIP")) : 0;  // tuning knob
     if (c->res_v2) CK(launch_rowres(A, p.math, c->res_nb, c->stream));
@@ -1095,6 +1093,34 @@ extern "C" uint64_t sq_lcg_jump(uint64_t seed, uint64_t gid0, uint64_t ndraws) {
 extern "C" int sq_slab_stats(sq_ctx *c, uint64_t *finder_scans, uint64_t *agree_rounds) {
     if (!c) return SQ_ERR_INVALID;
     sq_slab_stats_impl(c, finder_scans, agree_rounds);
+    return SQ_OK;
+}
+
+// ------------------------------------------------------------------- exact resume (f-1) ------
+extern "C" int sq_compat_get_state(sq_ctx *c, sq_compat_state *o) {
+    if (!c || !o || o->struct_size != sizeof(sq_compat_state) || c->p.kernel != SQ_KERNEL_COMPAT1D || c->pending) return SQ_ERR_INVALID;
+    int rc = sq_set_dev(c);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(&o->seed, c->c_seed, sizeof(u64), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&o->lrgEl, c->c_lrgEl, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&o->lrgVl, c->c_lrgVl, sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&o->omega, c->c_omega, sizeof(double), cudaMemcpyDeviceToHost));
+    if (o->lrgEl < 0 || o->lrgEl >= c->p.dims[0]) return SQ_ERR_INTERNAL;
+    CK(cudaMemcpy(&o->newf_lrgEl, c->c_newf + o->lrgEl, sizeof(double), cudaMemcpyDeviceToHost));
+    return SQ_OK;
+}
+extern "C" int sq_compat_set_state(sq_ctx *c, const sq_compat_state *s) {
+    if (!c || !s || s->struct_size != sizeof(sq_compat_state) || c->p.kernel != SQ_KERNEL_COMPAT1D || c->pending) return SQ_ERR_INVALID;
+    if (s->lrgEl < 0 || s->lrgEl >= c->p.dims[0]) return SQ_ERR_INVALID;
+    int rc = sq_set_dev(c);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(c->c_seed, &s->seed, sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->c_lrgEl, &s->lrgEl, sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->c_lrgVl, &s->lrgVl, sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->c_omega, &s->omega, sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->c_newf + s->lrgEl, &s->newf_lrgEl, sizeof(double), cudaMemcpyHostToDevice));
     return SQ_OK;
 }
 

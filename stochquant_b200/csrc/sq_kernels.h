@@ -194,7 +194,6 @@ struct ResidentArgs {
     unsigned *progress;   // [nblocks] steps completed by each CTA when it left
     // ---- row-parallel kernel (sq_rowres.cu) ----
     int rows_max;                       // rows per CTA (ceil(L1 / nblocks))
-    int debug;                          // timing experiments only (results are wrong): 1 no halo wait, 2 no CTA barrier wait
     unsigned long long *nclamp_slots;   // [RES_SLOTS] clamp hits per interval of RES_CKPT steps (committed for the
                                         // intervals that stand: an abandoned launch must not count twice)
 };

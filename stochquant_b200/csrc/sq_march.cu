@@ -22,8 +22,11 @@ namespace sq {
 #ifndef MARCH_MINB
 #define MARCH_MINB 4
 #endif
+#ifndef MARCH_MINB_RB
+#define MARCH_MINB_RB 3
+#endif
 template <int MATH, int NDIM, int POT, bool REBASE>
-__global__ void __launch_bounds__(256, REBASE ? 3 : MARCH_MINB) lattice_march_kernel(const LatticeArgs A) {
+__global__ void __launch_bounds__(256, REBASE ? MARCH_MINB_RB : MARCH_MINB) lattice_march_kernel(const LatticeArgs A) {
     if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;  // an earlier launch must be replayed
     const int chain = blockIdx.z;
     int tl;

@@ -51,6 +51,11 @@ class SqRngEntry(C.Structure):
                 ("ov_t1", C.c_uint64), ("ov_t2", C.c_uint64)]
 
 
+class SqCompatState(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("lrgEl", C.c_int32), ("seed", C.c_uint64),
+                ("lrgVl", C.c_double), ("omega", C.c_double), ("newf_lrgEl", C.c_double)]
+
+
 class SqFrameRec(C.Structure):
     _fields_ = [("dtau", C.c_double), ("stable", C.c_int32), ("steps", C.c_int32)]
 
@@ -140,6 +145,10 @@ def load() -> C.CDLL:
     L.sq_controller_get.argtypes = [vp, pd, C.POINTER(i64), C.POINTER(i32)]
     L.sq_frames.restype = i32
     L.sq_frames.argtypes = [vp, i32, i32, C.POINTER(SqFrameRec), pd]
+    L.sq_compat_get_state.restype = i32
+    L.sq_compat_get_state.argtypes = [vp, C.POINTER(SqCompatState)]
+    L.sq_compat_set_state.restype = i32
+    L.sq_compat_set_state.argtypes = [vp, C.POINTER(SqCompatState)]
     L.sq_session_open.restype = i32
     L.sq_session_open.argtypes = [C.POINTER(vp), C.c_char_p, i32, i32]
     L.sq_session_barrier.restype = i32
@@ -371,6 +380,19 @@ class Context:
         out = [(recs[k].dtau, recs[k].stable, recs[k].steps) for k in range(nframes)]
         self.runs = self.controller_get()[1]
         return out, xavg[:nframes]
+
+    def compat_state(self) -> dict:
+        """sq_compat_get_state: what the end file lacks for a bit-exact resume."""
+        st = SqCompatState()
+        st.struct_size = C.sizeof(SqCompatState)
+        self._check(self.L.sq_compat_get_state(self._h, C.byref(st)), "sq_compat_get_state")
+        return {k: getattr(st, k) for k, _ in SqCompatState._fields_ if k != "struct_size"}
+
+    def set_compat_state(self, seed, lrgEl, lrgVl, omega, newf_lrgEl):
+        st = SqCompatState()
+        st.struct_size = C.sizeof(SqCompatState)
+        st.seed, st.lrgEl, st.lrgVl, st.omega, st.newf_lrgEl = int(seed), int(lrgEl), lrgVl, omega, newf_lrgEl
+        self._check(self.L.sq_compat_set_state(self._h, C.byref(st)), "sq_compat_set_state")
 
     def kernel_timing(self, enable: bool):
         self._check(self.L.sq_kernel_timing(self._h, int(enable)), "sq_kernel_timing")

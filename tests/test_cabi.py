@@ -17,7 +17,7 @@ def test_header_symbols_exported(sq):
     nm = subprocess.run(["nm", "-D", "--defined-only", sq.library_path()], capture_output=True, text=True).stdout
     defined = set(re.findall(r" T (sq_[a-z0-9_]+)", nm))
     assert set(names) <= defined, sorted(set(names) - defined)
-    assert L.sq_api_version() == 2
+    assert L.sq_api_version() == 3
 
 
 def test_header_compiles_as_c(tmp_path):

@@ -94,3 +94,57 @@ def test_unwritable_end_file(gpu_sq, tmp_path):
     a = ["50", "0.1", "0.001", "2", "3", "1.0", "0", "1", "0", "5", "0", "/nonexistent_dir/out.txt", "40"]
     r = subprocess.run([EXE] + a, capture_output=True, cwd=str(tmp_path), timeout=120)
     assert r.returncode == 1 and r.stderr == b"Failed to write to Output.\n"  # tauhost.c:565-566
+
+
+def test_extended_trailer_resumes_bit_exactly(gpu_sq, tmp_path):
+    """SURVEY.md 8(f) f-1.  With TAUHOST_EXT_TRAILER=1 a run stopped after K frames and restarted from its end file
+    for K more leaves the SAME end file, byte for byte, as one run of 2K frames -- seed, omega, lrgEl / lrgVl, the
+    stale newf[lrgEl], the step size to the last bit and the controller's counter all travel in the trailer.  (The
+    double-well preset rejects ~45 frames first, so rollbacks, step-size changes and the stale newf[lrgEl] are all
+    exercised.)  Without the variable the restart behaves as the reference does (re-randomised omega and seed):
+    the end files then differ."""
+    K = 70
+    env = dict(os.environ, TAUHOST_EXT_TRAILER="1")
+    base = ["200", "0.02", "0.002", None, "3", "1.0", "2", "1", "0", "1000", None, None, "40"]
+
+    def run(frames, start, end, e):
+        a = list(base)
+        a[3], a[10], a[11] = str(frames), start, str(end)
+        r = subprocess.run([EXE] + a, capture_output=True, cwd=str(tmp_path), timeout=600, env=e)
+        assert r.returncode == 0, r.stderr.decode()
+        return r.stdout
+
+    whole, half, rest = tmp_path / "whole.txt", tmp_path / "half.txt", tmp_path / "rest.txt"
+    out_whole = run(2 * K, "0", whole, env)
+    run(K, "0", half, env)
+    out_rest = run(K, str(half), rest, env)
+    assert whole.read_bytes() == rest.read_bytes()
+    assert b"|sqext" in whole.read_bytes()
+    # the frame lines of the second half show the same data and step sizes (the percent column restarts)
+    lw, lr = out_whole.splitlines()[K:], out_rest.splitlines()
+    assert len(lw) == len(lr) == K
+    for u, v in zip(lw, lr):
+        assert u.rsplit(b"|", 1)[0] == v.rsplit(b"|", 1)[0]
+    # reference behaviour without the variable: the same restart re-randomises -> a different end file
+    plain = tmp_path / "plain.txt"
+    run(K, str(half), plain, dict(os.environ))
+    assert plain.read_bytes() != rest.read_bytes() and b"|sqext" not in plain.read_bytes()
+
+
+def test_stream_matches_golden(gpu_sq, tmp_path):
+    """The committed frame stream that tests/test_taumain_headless.py feeds to the reference's unmodified
+    front-end IS what the drop-in binary writes for taumain.py's own command line (first 40 frames): same
+    accept / reject sequence and step sizes, same data to 1e-6 (CUDA's logf / cosf / tanhf may move by an ulp
+    between toolkits, and log|xavg| of a value near zero amplifies it)."""
+    golden = open(os.path.join(ROOT, "tests", "golden", "tauhost_stream_40.txt"), "rb").read()
+    args = ["200", "0.02", "0.002", "40", "3", "1.0", "2", "1", "0", "1000", "0", str(tmp_path / "end.txt"), "40"]
+    r = subprocess.run([EXE] + args, capture_output=True, cwd=str(tmp_path), timeout=600)
+    assert r.returncode == 0, r.stderr.decode()
+    fg, fo = parse_stream(r.stdout), parse_stream(golden)
+    assert len(fg) == len(fo) == 40
+    assert r.stdout.splitlines()[0] == golden.splitlines()[0]
+    for (yg, dg, pg), (yo, do_, po) in zip(fg, fo):
+        assert dg == do_ and pg == po and yg.size == yo.size == 199
+        fin = np.isfinite(yo)
+        assert np.array_equal(fin, np.isfinite(yg))
+        assert np.allclose(np.exp(yg[fin]), np.exp(yo[fin]), rtol=0, atol=1e-6)

@@ -20,7 +20,15 @@ def io():
     L.th_initial_state.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, pd, pd, C.POINTER(C.c_ulong)]
     L.th_write_end_file.argtypes = [C.c_char_p, C.c_int, C.c_int, pd, pd, pd, pd, C.c_double, C.c_int, C.c_double]
     L.th_read_start_file.argtypes = [C.c_char_p, C.c_int, C.c_double, pd, pd, pd, pd, C.POINTER(C.c_int), pd]
+    L.th_write_end_file_ext.argtypes = [C.c_char_p, C.c_int, C.c_int, pd, pd, pd, pd, C.c_double, C.c_int, C.c_double, C.POINTER(ThExt)]
+    L.th_read_start_file_ext.argtypes = [C.c_char_p, C.c_int, C.c_double, pd, pd, pd, pd, C.POINTER(C.c_int), pd,
+                                         C.POINTER(ThExt), C.POINTER(C.c_int)]
     return L
+
+
+class ThExt(C.Structure):  # host/tauhost_io.h: th_ext
+    _fields_ = [("seed", C.c_ulonglong), ("lrgEl", C.c_int), ("stab_cnt", C.c_int), ("runs", C.c_longlong),
+                ("lrgVl", C.c_double), ("omega", C.c_double), ("newf_lrgEl", C.c_double), ("dtau", C.c_double)]
 
 
 def dp(a):
@@ -116,6 +124,46 @@ def test_end_file_bytes_and_round_trip(io, oracle, tmp_path):
         assert dt2.value == 1e-4  # tauhost.c:133-135
     assert io.th_read_start_file(b"/nonexistent/file", n, 1e-3, dp(xavg), dp(xx0), dp(x), dp(f), C.byref(rec), C.byref(dt)) == 1
     assert io.th_write_end_file(b"/nonexistent/dir/file", n, 40, dp(xavg), dp(xx0), dp(x), dp(f), 0., 0, 0.) == 1
+
+
+def test_extended_trailer_round_trip_and_reference_compat(io, oracle, tmp_path):
+    """the extended trailer sits BEHIND the reference's three trailer lines.  It round-trips
+    every field exactly (hex floats, u64 seed), the plain reader and the oracle's restatement of the reference's
+    reader (tauhost.c:116-168) read such a file exactly as if the trailer were not there, and a file without (or
+    with a truncated) trailer reports has_ext = 0."""
+    rng = np.random.default_rng(3)
+    n = 37
+    xavg, xx0, x, f = (rng.normal(size=n) for _ in range(4))
+    ext = ThExt(seed=2**64 - 12345, lrgEl=17, stab_cnt=7, runs=123456789012, lrgVl=1.0 / 3.0, omega=np.nextafter(2.0231, 3),
+                newf_lrgEl=-0.1 / 7.0, dtau=1.5e-4 / 0.95 / 0.95)
+    a, b = tmp_path / "ext.txt", tmp_path / "plain.txt"
+    p = lambda q: os.fsencode(str(q))
+    assert io.th_write_end_file_ext(p(a), n, 40, dp(xavg), dp(xx0), dp(x), dp(f), 2.0231, 123000, 1.5e-4, C.byref(ext)) == 0
+    assert io.th_write_end_file_ext(p(b), n, 40, dp(xavg), dp(xx0), dp(x), dp(f), 2.0231, 123000, 1.5e-4, None) == 0
+    ta, tb = a.read_bytes(), b.read_bytes()
+    assert ta.startswith(tb) and ta[len(tb):].startswith(b"1|sqext\n") and ta.count(b"\n") == tb.count(b"\n") + 9
+    oracle.lib().sqo_write_endfile(p(tmp_path / "o.txt"), n, 40, dp(xavg), dp(xx0), dp(x), dp(f), 2.0231, 123000, 1.5e-4)
+    assert tb == (tmp_path / "o.txt").read_bytes()  # ext == NULL is the reference's file, byte for byte
+    got, has = ThExt(), C.c_int(-1)
+    r = [np.zeros(n) for _ in range(4)]
+    rec, dt = C.c_int(-1), C.c_double(-1.0)
+    assert io.th_read_start_file_ext(p(a), n, 1e-3, dp(r[0]), dp(r[1]), dp(r[2]), dp(r[3]), C.byref(rec), C.byref(dt), C.byref(got), C.byref(has)) == 0
+    assert has.value == 1
+    for k, _ in ThExt._fields_:
+        assert getattr(got, k) == getattr(ext, k), k
+    assert all(np.array_equal(u, v) for u, v in zip(r, (xavg, xx0, x, f))) and rec.value == 123000 and dt.value == 1.5e-4
+    # the reference's reader (oracle restatement) and the plain reader ignore the trailer
+    for reader in (io.th_read_start_file, oracle.lib().sqo_read_startfile):
+        r2 = [np.zeros(n) for _ in range(4)]
+        rec2, dt2 = C.c_int(-1), C.c_double(-1.0)
+        assert reader(p(a), n, 1e-3, dp(r2[0]), dp(r2[1]), dp(r2[2]), dp(r2[3]), C.byref(rec2), C.byref(dt2)) == 0
+        assert all(np.array_equal(u, v) for u, v in zip(r2, (xavg, xx0, x, f))) and rec2.value == 123000 and dt2.value == 1.5e-4
+    # no trailer / truncated trailer -> has_ext = 0
+    for path, blob in ((b, tb), (tmp_path / "cut.txt", ta[:ta.rfind(b"\n", 0, len(ta) - 1) + 1])):
+        path.write_bytes(blob)
+        has.value = -1
+        assert io.th_read_start_file_ext(p(path), n, 1e-3, dp(r[0]), dp(r[1]), dp(r[2]), dp(r[3]), C.byref(rec), C.byref(dt), C.byref(got), C.byref(has)) == 0
+        assert has.value == 0
 
 
 def test_cli_forms_and_errors(tmp_path):
