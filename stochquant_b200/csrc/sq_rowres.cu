@@ -301,18 +301,15 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
 
     unsigned myclamp = 0, failed = 0;
     pair_t NZ[NP];
-    // Two step orders share one loop body.  A warp of kind "early" runs  noise(n) | wait B(n-1) | stencil(n) | arrive B(n):
-    // its noise phase fills the time the barrier needs.  A warp of kind "late" runs  noise(n) | stencil(n) | arrive B(n) |
-    // wait B(n): it arrives one noise phase later than the early warps (which are then busy with their next noise phase,
-    // so nobody waits longer), and the two kinds are in DIFFERENT phases at any moment: the integer / SFU work of one
-    // kind overlaps the shared-memory / packed-FP work of the other instead of 28 warps queueing for the same pipes.
-    // Every other warp of a scheduler is late; edge rows are early (their halo words travel during the noise phase).
-    const bool late = !EDGE && (((tid >> 5) >> 2) & 1);
+    // Step order of a warp:  noise(n) | wait B(n-1) | stencil(n) | arrive B(n).  The noise phase fills the time the
+    // barrier needs; an edge row's halo words are requested between the two and travel during the wait.  (Letting every
+    // other warp of a scheduler run one noise phase out of step with its siblings, so that the integer / SFU work of one
+    // overlaps the shared-memory / packed-FP work of the other, was measured: 491 against 506 G site-updates/s -- the
+    // warps de-phase by themselves.)
 
     // first barrier phase: everybody's initial row is in rowbuf[0]
     __syncwarp();
     if (lane == 0) mbar_arrive(mbar);
-    if (late) mbar_wait(mbar, 0);
 
     ulonglong2 pre[EDGE ? NP : 1];  // edge rows: halo words of the field in hand, requested before the barrier wait
     int n = 0, voided = 0;
@@ -324,7 +321,7 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
 #pragma unroll
             for (int i = 0; i < NP; ++i) pre[i] = ld_words(ps + 2 * i);
         }
-        if (!late) mbar_wait(mbar, par);  // phase n: B(n-1), the initial phase for n = 0
+        mbar_wait(mbar, par);  // phase n: B(n-1), the initial phase for n = 0
         if (REDUCER && n > 0) reduce_rows(n - 1, par ^ 1u);  // per-row sums of the field before step n-1
         // ---- rare: leave (flags written before the arrivals of the phase just waited for: the same answer in
         //      every thread of the CTA), checkpoint of the field before step n -----------------------------------
@@ -474,10 +471,9 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
             sts_u64(a_svc, lcg_next_seed(t2));
             if (!more) A.seed_out[0] = lcg_next_seed(t2);
         }
-        if (late) mbar_wait(mbar, par ^ 1u);  // phase n+1: B(n)
     }
     if (n == A.nsteps) {  // went through: the last step's sums, and was the last step void?
-        if (!late) mbar_wait(mbar, (unsigned)n & 1u);
+        mbar_wait(mbar, (unsigned)n & 1u);
         const unsigned fl = lds_f32_bits(flags_a + ((unsigned)n & 1u) * 4u);
         voided = (int)(fl >> 1);
         if (REDUCER && n > 0) reduce_rows(n - 1, ((unsigned)n & 1u) ^ 1u);
