@@ -6,7 +6,7 @@ NVCC  ?= nvcc
 ARCH  := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr
 CSRC  := stochquant_b200/csrc
-OBJS  := $(CSRC)/sq_api.o $(CSRC)/sq_compat1d.o $(CSRC)/sq_lattice.o $(CSRC)/sq_resident.o $(CSRC)/sq_rowres.o $(CSRC)/sq_march.o $(CSRC)/sq_tile.o $(CSRC)/sq_slab.o $(CSRC)/sq_session.o
+OBJS  := $(CSRC)/sq_api.o $(CSRC)/sq_compat1d.o $(CSRC)/sq_lattice.o $(CSRC)/sq_rowres.o $(CSRC)/sq_march.o $(CSRC)/sq_tile.o $(CSRC)/sq_slab.o $(CSRC)/sq_session.o
 HDRS  := include/sq.h $(CSRC)/sq_kernels.h $(CSRC)/sq_lcg.cuh $(CSRC)/sq_noise.cuh $(CSRC)/sq_site.cuh $(CSRC)/sq_ctx.h $(CSRC)/sq_session.h $(CSRC)/sq_lattice_common.cuh $(CSRC)/sq_pair.cuh $(CSRC)/sq_strip_slow.cuh
 
 all: stochquant_b200/libsq.so tauhost.o oracle

@@ -332,9 +332,14 @@ class Timer:
 
 
 def kernel_name(dims, real):
-    resident = len(dims) == 2 and real == "f32" and dims[0] % 128 == 0 and dims[0] <= 1024 and dims[1] <= 8 * 148
+    """the dominant kernel of a workload (mirrors the library's dispatch, sq_api.cu: init_lattice)"""
+    resident = False
+    if len(dims) == 2 and real == "f32" and dims[0] % 128 == 0 and dims[0] <= 1024 and dims[1] >= 2:
+        nb = min(148, dims[1] // 2)
+        rows = -(-dims[1] // nb)
+        resident = (dims[0] % 256 == 0 and rows * (dims[0] // 8) <= 896) or rows * (dims[0] // 4) <= 896
     if resident:
-        return "resident2d_kernel", True
+        return "rowres_kernel", True
     return ("lattice_march_kernel" if len(dims) >= 3 and real == "f32" else "lattice_step_kernel"), False
 
 

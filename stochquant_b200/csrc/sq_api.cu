@@ -304,16 +304,10 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
         const bool shape_ok = p.ndim == 2 && p.real == SQ_REAL_F32 && p.nchains == 1 && c->nt == Lt &&
                               L0 % 128 == 0 && L0 <= 1024 && !(p.flags & (SQ_FLAG_FORCE_STREAMING | SQ_FLAG_NO_OBSERVABLES));
         if (coop && shape_ok && sms > 0) {
-            int nb = (int)std::min<int64_t>(sms, L1);
-            int rows = (int)((L1 + nb - 1) / nb);
-            static const bool force_v1 = getenv("SQ_RESIDENT_V1") != nullptr;  // A/B knob: the round-1 band kernel
-            {   // the row-parallel kernel wants bands of at least two rows (each edge row has ONE neighbour CTA)
-                const int nb2 = (int)std::min<int64_t>(sms, L1 / 2);
-                const int rows2 = nb2 > 0 ? (int)((L1 + nb2 - 1) / nb2) : 0;
-                c->res_v2 = !force_v1 && nb2 > 0 && rowres_strip((int)L0, rows2) != 0;
-                if (c->res_v2) { nb = nb2; rows = rows2; }
-            }
-            if (c->res_v2 || rows <= RES_MAX_ROWS) {
+            // bands of at least two rows (each edge row has ONE neighbour CTA), at most 896 threads per CTA
+            const int nb = (int)std::min<int64_t>(sms, L1 / 2);
+            const int rows = nb > 0 ? (int)((L1 + nb - 1) / nb) : 0;
+            if (nb > 0 && rowres_strip((int)L0, rows) != 0) {
                 CK(preload_lattice_step(p.real, p.math, p.ndim));  // the event-recovery path: see sq_lattice.cu
                 c->res_ok = true;
                 c->res_nb = nb;
@@ -321,8 +315,8 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
                 if ((rc = dalloc(&c->r_halo, 2 * (size_t)nb * 2 * (size_t)L0))) return rc;
                 if ((rc = dalloc(&c->r_error, 1))) return rc;
                 if ((rc = dalloc(&c->r_progress, (size_t)nb))) return rc;
-                if ((rc = dalloc(&c->r_ckpt, 3 * (size_t)c->V))) return rc;
-                // one allocation: hist_rows[RES_MAX_STEPS][L1], then hist_p2 (per row for the row-parallel kernel, per CTA before)
+                if ((rc = dalloc(&c->r_ckpt, (size_t)RES_NCKPT * (size_t)c->V))) return rc;
+                // one allocation: hist_rows[RES_MAX_STEPS][L1], then hist_p2[RES_MAX_STEPS][L1]
                 if ((rc = dalloc(&c->r_hist_rows, 2 * (size_t)RES_MAX_STEPS * (size_t)L1))) return rc;
                 c->r_hist_p2 = c->r_hist_rows + (size_t)RES_MAX_STEPS * (size_t)L1;
                 if ((rc = dalloc(&c->r_nclamp_slots, (size_t)RES_SLOTS))) return rc;
@@ -603,9 +597,7 @@ static int enqueue_resident(sq_ctx *c, double dtau, int nsteps, int64_t runs0) {
     if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     A.rows_max = c->res_rows;
     A.nclamp_slots = c->r_nclamp_slots;
-    static const int strip_w = getenv("SQ_RESIDENT_STRIP") ? atoi(getenv("SQ_RESIDENT_STRIP")) : 0;  // tuning knob
-    if (c->res_v2) CK(launch_rowres(A, p.math, c->res_nb, c->stream));
-    else CK(launch_resident2d(A, p.math, c->res_nb, c->res_rows, strip_w, c->stream));
+    CK(launch_rowres(A, p.math, c->res_nb, c->stream));
     if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     c->launches++;
     return enqueue_resident_welford(c, nsteps, runs0);
@@ -618,7 +610,7 @@ static int enqueue_resident_welford(sq_ctx *c, int nsteps, int64_t runs0) {
     W.nt = c->nt;
     W.nsteps = nsteps;
     W.tmid = (int)(p.dims[1] / 2);
-    W.np2 = c->res_v2 ? (int)p.dims[1] : c->res_nb;  // partial sums of phi^2: per row | per CTA
+    W.np2 = (int)p.dims[1];  // partial sums of phi^2: per row
     W.vslice = c->vslice;
     W.runs = runs0;
     W.hist_rows = c->r_hist_rows;
@@ -631,7 +623,7 @@ static int enqueue_resident_welford(sq_ctx *c, int nsteps, int64_t runs0) {
     W.event_key = c->l_event;
     CK(launch_welford_history(W, c->r_step_sums, c->stream));
     c->launches += 2;
-    if (c->res_v2) {  // clamp hits of the checkpoint intervals that stand (none of them while an event is flagged)
+    {   // clamp hits of the checkpoint intervals that stand (none of them while an event is flagged)
         CK(launch_commit_clamps(c->r_nclamp_slots, (nsteps + RES_CKPT - 1) / RES_CKPT, RES_SLOTS, c->l_nclamped, c->l_event, c->stream));
         c->launches++;
     }
@@ -737,7 +729,7 @@ static int sync_lattice(sq_ctx *c) {
                     const u64 none = NO_EVENT;
                     CK(cudaMemcpy(c->l_event, &none, sizeof(u64), cudaMemcpyHostToDevice));
                     key = NO_EVENT;  // (already cleared: skip the reset below)
-                    CK(cudaMemcpyAsync(c->l_field[c->cur], c->r_ckpt + (size_t)((c0 / RES_CKPT) % 3) * (size_t)c->V,
+                    CK(cudaMemcpyAsync(c->l_field[c->cur], c->r_ckpt + (size_t)((c0 / RES_CKPT) % RES_NCKPT) * (size_t)c->V,
                                        sizeof(float) * (size_t)c->V, cudaMemcpyDeviceToDevice, c->stream));
                     u64 S;  // the step-start seed, c0 event-free steps on (what the kernel's omega thread does)
                     CK(cudaMemcpy(&S, c->l_seeds[c->cur], sizeof(u64), cudaMemcpyDeviceToHost));
@@ -753,7 +745,7 @@ static int sync_lattice(sq_ctx *c) {
                     done += c0;
                     runs0 += c0;
                     k -= c0;
-                } else if (c->res_v2) {  // nothing stands: drop the abandoned launch's clamp counts
+                } else {  // nothing stands: drop the abandoned launch's clamp counts
                     CK(launch_commit_clamps(c->r_nclamp_slots, 0, RES_SLOTS, c->l_nclamped, nullptr, c->stream));
                     c->launches++;
                 }

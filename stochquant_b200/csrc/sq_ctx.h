@@ -26,7 +26,6 @@ struct SlabState;      // sq_slab.cu
 constexpr int MAX_SEQ_STEPS = 32768;  // step field of the event key has 16 bits
 constexpr int MAX_REBASE = 64;
 constexpr int RES_MAX_STEPS = 2048;  // tau-steps per resident launch (history buffer)
-constexpr int RES_MAX_ROWS = 8;
 
 struct sq_ctx {
     using JumpEntry = sq::JumpEntry;
@@ -84,12 +83,11 @@ struct sq_ctx {
     JumpEntry *l_cta_jump = nullptr, *l_thr_jump = nullptr;
     // resident 2-D path (sq_resident.cu)
     bool res_ok = false;
-    bool res_v2 = false;    // row-parallel kernel (sq_rowres.cu); false: the round-1 band kernel (sq_resident.cu)
     int res_nb = 0, res_rows = 0;
     unsigned long long *r_nclamp_slots = nullptr;  // [RES_SLOTS] clamp hits per checkpoint interval of a resident launch
     unsigned long long *r_halo = nullptr;
     unsigned *r_error = nullptr, *r_progress = nullptr;
-    float *r_ckpt = nullptr;  // [3][V] checkpoints of the resident kernel (RNG-event recovery)
+    float *r_ckpt = nullptr;  // [RES_NCKPT][V] checkpoints of the resident kernel (RNG-event recovery)
     unsigned r_tag = 1;     // monotonic halo tag base (never reused, also across replays)
     double *r_hist_rows = nullptr, *r_hist_p2 = nullptr, *r_step_sums = nullptr;
     int res_limit = 0;      // >0: the next resident batch must stop after this many steps

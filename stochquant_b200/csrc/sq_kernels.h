@@ -184,24 +184,24 @@ struct ResidentArgs {
     unsigned long long *nclamped;
     unsigned *error_flag;
     // RNG-event recovery: every RES_CKPT steps each CTA drops its band (the field BEFORE step n,
-    // n a multiple of RES_CKPT) into ckpt[(n / RES_CKPT) % 3]; a CTA that sees the event word raised
+    // n a multiple of RES_CKPT) into ckpt[(n / RES_CKPT) % RES_NCKPT]; a CTA that sees the event word raised
     // stops and records how far it got.  The host resumes from the last checkpoint every CTA has
     // written instead of from the start of the launch (CTA skew is bounded by the halo dependency:
-    // at most nblocks/2 steps, far less than 2 * RES_CKPT).
+    // at most nblocks/2 = 74 steps, far less than (RES_NCKPT - 1) * RES_CKPT = 224).
     u64 row_const[8];     // k * L0 * A: the site constant gid*A+B of row k relative to the band's first row
     unsigned one;         // 1, from the host: a multiplier ptxas cannot fold (sq_site.cuh: site_const_next)
-    float *ckpt;          // [3][L1][L0]
+    float *ckpt;          // [RES_NCKPT][L1][L0]
     unsigned *progress;   // [nblocks] steps completed by each CTA when it left
     // ---- row-parallel kernel (sq_rowres.cu) ----
     int rows_max;                       // rows per CTA (ceil(L1 / nblocks))
     unsigned long long *nclamp_slots;   // [RES_SLOTS] clamp hits per interval of RES_CKPT steps (committed for the
                                         // intervals that stand: an abandoned launch must not count twice)
 };
-constexpr int RES_CKPT = 128;
-constexpr int RES_SLOTS = 16;  // RES_MAX_STEPS / RES_CKPT
+constexpr int RES_CKPT = 32;    // steps between checkpoints: an RNG event costs a re-run of 16 steps on average
+constexpr int RES_NCKPT = 8;    // checkpoint ring
+constexpr int RES_SLOTS = 64;   // RES_MAX_STEPS / RES_CKPT
 int rowres_strip(int L0, int rows_max);  // sites per thread (8 | 4), 0: shape not eligible
 cudaError_t launch_rowres(const ResidentArgs &A, int math, int nblocks, cudaStream_t st);
-cudaError_t launch_resident2d(const ResidentArgs &A, int math, int nblocks, int rows_max, int strip_w, cudaStream_t st);
 
 struct WelfordArgs {
     int nt, nsteps, tmid, np2;

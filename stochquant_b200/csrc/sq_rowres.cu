@@ -329,7 +329,7 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
         if (__builtin_expect((fl != 0u) | (((unsigned)n & (RES_CKPT - 1)) == 0u), 0)) {
             voided = (int)(fl >> 1);
             if (n > 0 && !voided && ((unsigned)n & (RES_CKPT - 1)) == 0u) {
-                float *dst = A.ckpt + (size_t)((n / RES_CKPT) % 3) * (size_t)A.V + (size_t)(r0 + k) * L0 + W * j;
+                float *dst = A.ckpt + (size_t)((n / RES_CKPT) % RES_NCKPT) * (size_t)A.V + (size_t)(r0 + k) * L0 + W * j;
 #pragma unroll
                 for (int h = 0; h < NH; ++h) checkpoint4_cold(dst + 4 * h, PH[2 * h], PH[2 * h + 1]);
                 if (myclamp) atomicAdd(A.nclamp_slots + (n / RES_CKPT - 1), (unsigned long long)myclamp);
@@ -554,6 +554,86 @@ __global__ void __launch_bounds__(ROWRES_THREADS, 1) rowres_kernel(const Residen
     else if (edge == 1) { if (reducer) SQ_ROLE(1, true); else SQ_ROLE(1, false); }
     else { if (reducer) SQ_ROLE(2, true); else SQ_ROLE(2, false); }
 #undef SQ_ROLE
+}
+
+// ---- history of a launch -> running means -----------------------------------------------------------------
+// per-step global sums of the history: one warp per step -> step_sums[n] = (sum phi, sum phi^2)
+__global__ void __launch_bounds__(256) history_sums_kernel(const WelfordArgs A, double *step_sums) {
+    if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), l = threadIdx.x & 31;
+    if (n >= A.nsteps) return;
+    double s1 = 0, s2 = 0;
+    for (int k = l; k < A.nt; k += 32) s1 += A.hist_rows[(size_t)n * A.nt + k];
+    for (int k = l; k < A.np2; k += 32) s2 += A.hist_p2[(size_t)n * A.np2 + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (l == 0) {
+        step_sums[2 * n] = s1;
+        step_sums[2 * n + 1] = s2;
+    }
+}
+
+// history -> running means (tau_kernel.cl:144-145 per time slice).  The reference's update
+// x <- x + (v - x)/(runs+j+1) is the running mean, so n more samples give, in closed form,
+//     x' = x + (sum_j v_j - n x) / (runs + n):
+// two sums per slice over the launch's steps instead of a sequential recurrence (fp64 rounding differs
+// from the step-by-step form at the 1e-15 level; the parity tolerance on these observables is 1e-3).
+// One thread per slice, loads batched so their latencies overlap; fixed summation order.  (Splitting the
+// step range over four warps per slice block was measured slower.)
+__global__ void __launch_bounds__(128) welford_history_kernel(const WelfordArgs A, const double *step_sums) {
+    if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const double inv_vs = 1.0 / (double)A.vslice;
+    const double n = (double)A.nsteps, den = (double)(A.runs + A.nsteps);
+    if (t < A.nt) {
+        constexpr int B = 16;
+        double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, last = 0;
+        for (int n0 = 0; n0 < A.nsteps; n0 += B) {
+            double h[B], hm[B];
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+                const int k = min(n0 + j, A.nsteps - 1);
+                h[j] = A.hist_rows[(size_t)k * A.nt + t];
+                hm[j] = A.hist_rows[(size_t)k * A.nt + A.tmid];
+            }
+#pragma unroll
+            for (int j = 0; j < B; ++j)
+                if (n0 + j < A.nsteps) {
+                    s1[j & 3] += h[j];
+                    s2[j & 3] = fma(h[j], hm[j], s2[j & 3]);
+                    last = h[j];
+                }
+        }
+        const double SP = ((s1[0] + s1[1]) + (s1[2] + s1[3])) * inv_vs;
+        const double SPP = ((s2[0] + s2[1]) + (s2[2] + s2[3])) * inv_vs * inv_vs;
+        const double x = A.slice_x[t], xx0 = A.slice_xx0[t];
+        A.slice_x[t] = x + (SP - n * x) / den;
+        A.slice_xx0[t] = xx0 + (SPP - n * xx0) / den;
+        A.slice_sum[t] = last;
+    }
+    if (t == A.nt) {  // one spare thread: running means of <phi>, <phi^2>
+        const double inv_vol = 1.0 / ((double)A.vslice * (double)A.nt);
+        double a1 = 0, a2 = 0, s1 = 0, s2 = 0;
+        for (int k = 0; k < A.nsteps; ++k) {
+            s1 = step_sums[2 * k];
+            s2 = step_sums[2 * k + 1];
+            a1 += s1;
+            a2 += s2;
+        }
+        A.sums[0] = s1;
+        A.sums[1] = s2;
+        A.sums_mean[0] += (a1 * inv_vol - n * A.sums_mean[0]) / den;
+        A.sums_mean[1] += (a2 * inv_vol - n * A.sums_mean[1]) / den;
+    }
+}
+
+cudaError_t launch_welford_history(const WelfordArgs &A, double *step_sums, cudaStream_t stream) {
+    history_sums_kernel<<<(A.nsteps + 7) / 8, 256, 0, stream>>>(A, step_sums);
+    welford_history_kernel<<<(A.nt + 1 + 31) / 32, 32, 0, stream>>>(A, step_sums);
+    return cudaGetLastError();
 }
 
 template <int MATH, int POT, int NP>
