@@ -438,6 +438,27 @@ def ring_parity(sq, np, torch, dist, world, rank, local):
     return verdict
 
 
+def nvlink_bytes(local):
+    """NVLink data bytes (tx, rx) of this rank's GPU since driver load, summed over its links (NVML field values, KiB
+    counters); None where the driver does not report them."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ids = [pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX]
+        vals = pynvml.nvmlDeviceGetFieldValues(h, ids)
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                return None
+            out.append(int(v.value.ullVal) * 1024)
+        return out
+    except Exception:
+        return None
+
+
 def ring_block(sq, np, torch, dist, timer, world, rank, local, args):
     """configs[3] inside the multi-GPU line: the 256^4 ring on all ranks, then -- on rank 0 alone, the other GPUs
     idle -- the same slab volume as a ring of one (finder + halo protocol, no NVLink) and as a plain context."""
@@ -459,8 +480,10 @@ def ring_block(sq, np, torch, dist, timer, world, rank, local, args):
     for _ in range(warm):
         ctx.step(dtau, loops)
     barrier()
+    nv0 = nvlink_bytes(local)
     ms = timer.frames(ctx, dtau, loops, steps, 0)
     barrier()
+    nv1 = nvlink_bytes(local)
     t = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
@@ -480,6 +503,10 @@ def ring_block(sq, np, torch, dist, timer, world, rank, local, args):
                "unit": "site-updates/s", "ms_per_step": total_ms / steps, "steps": steps, "tau_steps_per_step": loops,
                "update_kernel_us": kus, "roofline_frac": vloc * 8 / (kus * 1e-6) / 1e9 / peak,
                "halo_bytes_per_tau_step_per_rank": {"sent": 2 * (V // dims[-1]) * 4, "received": 2 * (V // dims[-1]) * 4},
+               # NVML's NVLink data counters of rank 0's GPU around the timed frames (includes the L2 flushes' nothing: the
+               # flush is local) -- the halo slices are the only peer traffic of the run
+               "nvlink_bytes_per_tau_step_rank0": ({"tx": (nv1[0] - nv0[0]) / (steps * loops), "rx": (nv1[1] - nv0[1]) / (steps * loops),
+                                                    "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX field values"} if nv0 and nv1 else None),
                "finder_scans_per_tau_step": stats["finder_scans"] / nsteps_total,
                "agree_rounds_per_tau_step": stats["agree_rounds"] / nsteps_total,
                "ring_parity": parity,

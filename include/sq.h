@@ -79,7 +79,9 @@ typedef struct sq_params {
     /* slab decomposition along the time axis (LATTICE): this context owns global
      * time slices [slab_t0, slab_t0+slab_nt).  0,0 = the whole lattice.          */
     int64_t slab_t0, slab_nt;
-    int32_t steps_per_launch; /* LATTICE: tau-steps fused per launch (0 = auto)   */
+    int32_t reserved;         /* 0.  (Was steps_per_launch in API 2, never read: the library chooses the fusion itself --
+                                 a whole frame per launch on chip for 2-D lattices that fit, one step per launch for the
+                                 streaming kernels, which are instruction-bound, not HBM-bound: DESIGN.md section 8.) */
     int32_t flags;            /* SQ_FLAG_*                                        */
 } sq_params;
 

@@ -32,7 +32,7 @@ class SqParams(C.Structure):
                 ("dims", C.c_int64 * 4), ("spacing", C.c_double), ("noise_c", C.c_double),
                 ("m2", C.c_double), ("lam", C.c_double), ("device", C.c_int32),
                 ("nchains", C.c_int32), ("slab_t0", C.c_int64), ("slab_nt", C.c_int64),
-                ("steps_per_launch", C.c_int32), ("flags", C.c_int32)]
+                ("reserved", C.c_int32), ("flags", C.c_int32)]
 
 
 class SqObs(C.Structure):
@@ -246,7 +246,7 @@ class Context:
 
     def __init__(self, dims, kernel="lattice", real="f32", math="accurate", potential=0,
                  spacing=1.0, noise_c=1.0, m2=0.0, lam=0.0, device=0, nchains=1, seed=1242608872,
-                 f0=None, x0=None, xx0_0=None, omega0=0.0, slab=(0, 0), flags=0, steps_per_launch=0):
+                 f0=None, x0=None, xx0_0=None, omega0=0.0, slab=(0, 0), flags=0):
         self.L = load()
         dims = [int(d) for d in (dims if hasattr(dims, "__len__") else [dims])]
         p = SqParams()
@@ -263,7 +263,7 @@ class Context:
         p.spacing, p.noise_c, p.m2, p.lam = spacing, noise_c, m2, lam
         p.device, p.nchains = device, nchains
         p.slab_t0, p.slab_nt = slab
-        p.flags, p.steps_per_launch = flags, steps_per_launch
+        p.flags, p.reserved = flags, 0
         self.params = p
         self.dims = dims
         self.kernel = kernel
