@@ -12,6 +12,10 @@
 
 #include "sq_ctx.h"
 
+#ifndef SQ_TILE_DEFAULT
+#define SQ_TILE_DEFAULT 4  // streaming fp32 d >= 3, event-free steps: 4 = tile kernel (sq_tile.cu), 0 = marching kernel only
+#endif
+
 using namespace sq;
 
 static thread_local char g_cuda_err_tls[512] = "";
@@ -194,39 +198,39 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
     int64_t cps = (nstrips + 256 * 4 - 1) / (256 * 4);
     if (cps < 1) cps = 1;
     c->ctas_per_slice = (int)std::min<int64_t>(cps, 65535);
-    // row-marching kernel (sq_march.cu): fp32, d >= 3, dims[0]/4 threads per row a power of two
+    // fp32, d >= 3: the row-marching kernel (sq_march.cu; 4-site strips, dims[0]/4 threads per row a power of two) or the tile
+    // kernel (sq_tile.cu; 8- or 4-site strips, tiles of 4 / 8 / 16 rows per thread that are whole planes or divide one, at
+    // most 72 KB of shared memory)
     if (p.real == SQ_REAL_F32 && p.ndim >= 3 && !(p.flags & SQ_FLAG_GENERIC_KERNEL)) {
-        const int64_t L0 = p.dims[0], L1 = p.dims[1], tpr = L0 / 4;
-        if (L0 % 4 == 0 && tpr >= 1 && tpr <= 256 && (tpr & (tpr - 1)) == 0) {
-            const int64_t rg = 256 / tpr, nrows = c->vslice / L0;
-            int best = 0;
-            static const int force_R = getenv("SQ_MARCH_R") ? atoi(getenv("SQ_MARCH_R")) : 0;  // tuning knob
-            // The tile kernel is correct (the whole GPU suite passes on it) and executes fewer instructions (50 against 58
-            // per site) but is SLOWER than the marching kernel on every measured shape (256^3 slices 334 against 375 G
-            // site-updates/s, 64^4 287 / 305, 32^4 chains 264 / 300): 24 instead of 32 warps per SM, a staging bubble at
-            // the start of every CTA and four global streams with one pass of lookahead.  It is kept behind SQ_TILE=1
-            // for the next round's persistent / multi-stage version; the marching kernel is the default.
-            static const bool no_tile = getenv("SQ_TILE") == nullptr;
+        const int64_t L0 = p.dims[0], L1 = p.dims[1], nrows = c->vslice / L0;
+        static const int force_R = getenv("SQ_MARCH_R") ? atoi(getenv("SQ_MARCH_R")) : 0;    // tuning knob
+        static const int tile_w = getenv("SQ_TILE") ? (atoi(getenv("SQ_TILE")) ? 4 : 0) : SQ_TILE_DEFAULT;  // 0: marching kernel only, 4: tile kernel
+        int best = 0, best_w = 4;
+        for (int attempt = 0; attempt < 3 && !best; ++attempt) {
+            // attempt 0: tile kernel with the requested strip width; 1: tile kernel with 4-site strips; 2: marching kernel
+            const bool tile = attempt < 2;
+            const int w = attempt == 0 ? tile_w : 4;
+            if (tile && (tile_w == 0 || (attempt == 1 && tile_w == 4))) continue;
+            if (w != 4 && w != 8) continue;
+            const int64_t tpr = L0 / w;
+            if (L0 % w != 0 || tpr < 1 || tpr > 256 || (tpr & (tpr - 1)) != 0) continue;
+            const int64_t rg = 256 / tpr;
             int tlog = 0;
             while ((1 << tlog) < tpr) tlog++;
-            // the tile kernel (sq_tile.cu) stages a CTA's rows in shared memory: 4, 8 or 16 rows per thread, tiles that are
-            // whole planes or divide one, at most 72 KB; otherwise the marching kernel takes the shape
-            for (int pass = no_tile ? 1 : 0; pass < 2 && !best; ++pass) {
-                const bool tile = pass == 0;
-                for (int R = force_R ? force_R : 16; R >= 1; R >>= 1) {
-                    if (L1 % R != 0 || nrows % (rg * R) != 0) continue;
-                    if (tile && !tile_shape_ok((int)L0, (int)L1, tlog, R)) continue;
-                    const int64_t ctas = nrows / (rg * R) * c->nt * p.nchains;
-                    best = R;  // the largest that fits, unless a smaller one is needed to fill the GPU
-                    if (ctas >= 148 * 12) break;
-                }
-                c->tile_ok = tile && best != 0;
+            for (int R = force_R ? force_R : 16; R >= 1; R >>= 1) {
+                if (L1 % R != 0 || nrows % (rg * R) != 0 || nrows / (rg * R) > 65535) continue;
+                if (tile && !tile_shape_ok((int)L0, (int)L1, tlog, R)) continue;
+                const int64_t ctas = nrows / (rg * R) * c->nt * p.nchains;
+                best = R;  // the largest that fits, unless a smaller one is needed to fill the GPU
+                best_w = w;
+                if (ctas >= 148 * 12) break;
             }
-            if (best && nrows / (rg * best) <= 65535) {
+            if (best) {
                 c->march_ok = true;
+                c->tile_ok = tile;
                 c->m_R = best;
-                c->m_tpr_log = 0;
-                while ((1 << c->m_tpr_log) < tpr) c->m_tpr_log++;
+                c->m_w = best_w;
+                c->m_tpr_log = tlog;
                 c->ctas_per_slice = (int)(nrows / (rg * best));
             }
         }
@@ -272,10 +276,10 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
         CK(cudaMemcpy(c->l_slice_jump, sj.data(), sizeof(JumpEntry) * sj.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->l_strip_jump, qj.data(), sizeof(JumpEntry) * qj.size(), cudaMemcpyHostToDevice));
         if (c->march_ok) {
-            const u64 L0 = (u64)p.dims[0], tpr = L0 / 4, rows_per_cta = (256 / tpr) * (u64)c->m_R;
+            const u64 L0 = (u64)p.dims[0], tpr = L0 / (u64)c->m_w, rows_per_cta = (256 / tpr) * (u64)c->m_R;
             std::vector<JumpEntry> cj((size_t)c->ctas_per_slice), tj(256);
             for (size_t b = 0; b < cj.size(); ++b) cj[b] = jump_entry((u64)b * rows_per_cta * L0);
-            for (u64 t = 0; t < 256; ++t) tj[t] = jump_entry((t / tpr) * (u64)c->m_R * L0 + (t % tpr) * 4);
+            for (u64 t = 0; t < 256; ++t) tj[t] = jump_entry((t / tpr) * (u64)c->m_R * L0 + (t % tpr) * (u64)c->m_w);
             CK(cudaMalloc((void **)&c->l_cta_jump, sizeof(JumpEntry) * cj.size()));
             CK(cudaMalloc((void **)&c->l_thr_jump, sizeof(JumpEntry) * tj.size()));
             CK(cudaMemcpy(c->l_cta_jump, cj.data(), sizeof(JumpEntry) * cj.size(), cudaMemcpyHostToDevice));
@@ -460,8 +464,9 @@ LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */
     A.jump = c->d_jump;
     A.m_on = c->march_ok ? (c->tile_ok ? 2 : 1) : 0;
     A.t_dck = LCG_BETA * (u64)p.dims[0] * jump_entry((u64)p.dims[0]).g0;
-    A.t_dc1 = (u64)(p.dims[0] - 3) * LCG_A;
-    A.t_dc2 = (u64)(p.dims[0] - 3) * LCG_BETA;
+    A.m_w = c->m_w;
+    A.t_dc1 = (u64)(p.dims[0] - (c->m_w - 1)) * LCG_A;   // from a strip's last site to the next row's first
+    A.t_dc2 = (u64)(p.dims[0] - (c->m_w - 1)) * LCG_BETA;
     A.m_R = c->m_R;
     A.m_tpr_log = c->m_tpr_log;
     A.cta_jump = c->l_cta_jump;
@@ -476,7 +481,7 @@ LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */
 }
 
 int sq_launch_update(sq_ctx *c, const LatticeArgs &A) {
-    if (A.m_on == 2) CK(launch_lattice_tile(A, c->p.math, c->ctas_per_slice, c->stream));
+    if (A.m_on == 2 && A.n_rebase == 0) CK(launch_lattice_tile(A, c->p.math, c->ctas_per_slice, c->stream));  // (entries: marching kernel)
     else if (A.m_on) CK(launch_lattice_march(A, c->p.math, c->ctas_per_slice, c->stream));
     else CK(launch_lattice_step(A, c->p.real, c->p.math, c->ctas_per_slice, c->stream));
     return SQ_OK;

@@ -79,7 +79,7 @@ struct sq_ctx {
     // row-marching kernel (sq_march.cu): geometry + jump tables, when the shape qualifies
     bool march_ok = false;
     bool tile_ok = false;   // ... and its tiles can be staged in shared memory: lattice_tile_kernel (sq_tile.cu)
-    int m_R = 0, m_tpr_log = 0;
+    int m_R = 0, m_tpr_log = 0, m_w = 4;
     JumpEntry *l_cta_jump = nullptr, *l_thr_jump = nullptr;
     // resident 2-D path (sq_resident.cu)
     bool res_ok = false;

@@ -112,9 +112,10 @@ struct LatticeArgs {
     // ---- row-marching kernel (sq_march.cu), fp32 d = 3,4 with dims[0]/4 a power of two <= 256 ----
     int m_on;                    // 1: launch lattice_march_kernel (gridDim.x = its own CTAs per slice), 2: lattice_tile_kernel
     int m_R;                     // consecutive rows (x1) per thread; divides dims[1]
-    int m_tpr_log;               // log2(threads per row) = log2(dims[0] / 4)
+    int m_w;                     // sites per strip: 4 (marching kernel, tile kernel) or 8 (tile kernel)
+    int m_tpr_log;               // log2(threads per row) = log2(dims[0] / m_w)
     const JumpEntry *cta_jump;   // [ctas per slice] jump over bx * rows_per_cta * L0 draws
-    const JumpEntry *thr_jump;   // [256] jump over (ty * R * L0 + tx * 4) draws
+    const JumpEntry *thr_jump;   // [256] jump over (ty * R * L0 + tx * m_w) draws
     JumpEntry row_jump;          // jump over L0 draws (one row down at fixed x0)
     u64 t_dck, t_dc1, t_dc2;     // tile kernel: per-row increments of the affine constant and of the two site constants
     // ---- multi-GPU slab ring (sq_slab.cu); slab_on == 0: everything below is unused ----------

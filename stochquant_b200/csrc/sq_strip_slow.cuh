@@ -10,6 +10,7 @@ namespace {
 
 struct Draws {
     unsigned u1[4], u2[4];
+    u64 s_after;  // seed behind the four draws (48 bits)
 };
 
 // generic draws of one strip under the step's replay entries (a strip that contains an entry's
@@ -37,6 +38,7 @@ __device__ __noinline__ Draws draws_slow(const RebaseEntry *rebase, int n_rebase
         d.u1[e] = (unsigned)(t1 >> 16);
         d.u2[e] = (unsigned)(t2 >> 16);
     }
+    d.s_after = s;
     return d;
 }
 
@@ -56,6 +58,7 @@ struct SlowIn {
 struct SlowOut {
     float a1, a2;
     unsigned nclamp;
+    u64 s_after;  // seed behind the strip's four draws: a wider strip continues from here
 };
 template <int MATH, int NDIM, int POT>
 __device__ __noinline__ SlowOut strip_slow(const SlowIn I) {
@@ -74,6 +77,7 @@ __device__ __noinline__ SlowOut strip_slow(const SlowIn I) {
                 nd2[4] = {d2.x, d2.y, d2.z, d2.w}, ntp[4] = {tp.x, tp.y, tp.z, tp.w}, ntm[4] = {tm.x, tm.y, tm.z, tm.w};
     const float kth = (float)(2.0 * 3.1415 / 4294967296.0);
     SlowOut r;
+    r.s_after = d.s_after;
     r.a1 = 0.f;
     r.a2 = 0.f;
     r.nclamp = 0;
@@ -124,7 +128,7 @@ struct Rebased {
     bool slow;       // an entry's gid_start or overridden site (= gid_start - 1) lies inside the strip
 };
 __device__ __forceinline__ Rebased rebase_eval(const RebaseEntry *rebase, int n_rebase, int chain, u64 S, u64 g0, u64 gslice,
-                                               unsigned vs) {
+                                               unsigned vs, unsigned w = 4u /* sites per strip */) {
     Rebased r;
     r.S_eff = S;
     r.cnt = 0;
@@ -137,8 +141,8 @@ __device__ __forceinline__ Rebased rebase_eval(const RebaseEntry *rebase, int n_
             r.cnt++;
             if (gs >= bg) { bg = gs; r.S_eff = rebase[j].vseed; }
         }
-        r.slow |= (gs - g0 <= 4ULL);
-        if (gs > g0 + 4 && gs < nxt) nxt = gs;
+        r.slow |= (gs - g0 <= (u64)w);
+        if (gs > g0 + w && gs < nxt) nxt = gs;
     }
     r.nxt32 = (nxt - gslice < (u64)vs) ? (unsigned)(nxt - gslice) : 0x7FFFFFFFu;
     return r;

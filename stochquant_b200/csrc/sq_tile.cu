@@ -15,7 +15,10 @@
 //     consumed after the pass's noise phase: the draws and the Box-Muller arithmetic (2/3 of the instructions,
 //     no field data) run while they are in flight.  Their addresses are per-thread 64-bit bases + an immediate
 //     (the row stride is a template parameter for rows of 32 / 64 / 256 sites);
-//   * the LCG is walked in its t2 form (see sq_rowres.cu): two independent 48-bit multiply-adds per site.
+//   * the LCG is walked in its t2 form (see sq_rowres.cu): two independent 48-bit multiply-adds per site;
+//   * a thread's strip is EIGHT consecutive sites where the row length allows (four otherwise): what is paid per
+//     strip -- the row-to-row advance of the chain, the x0 neighbours, the rare-case tests, the stream addresses --
+//     halves, and the noise phase that covers the global loads' latency doubles.
 // CTA -> tile mapping, jump tables, per-CTA observable partials, clamp slots, replay entries (REBASE), L2
 // chunking and the slab ring's halo protocol are those of the marching kernel, so the host side is shared.
 #include "sq_strip_slow.cuh"
@@ -73,12 +76,14 @@ __device__ __forceinline__ void tile_mbar_wait(unsigned bar, unsigned parity) {
 }  // namespace
 
 // L0T: row length known at compile time (0: runtime) -- the byte stride between a thread's passes becomes an immediate
+// NP: packed pairs per strip (2: four sites, 4: eight sites per thread and pass)
 // REBASE: the step has replay entries (the common, event-free instance carries none of that code)
-template <int MATH, int NDIM, int POT, int L0T, bool REBASE>
 #ifndef TILE_MINB
 #define TILE_MINB 3
 #endif
-__global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kernel(const LatticeArgs A) {
+template <int MATH, int NDIM, int POT, int L0T, int NP, bool REBASE>
+__global__ void __launch_bounds__(256, NP == 4 ? 2 : (REBASE ? 3 : TILE_MINB)) lattice_tile_kernel(const LatticeArgs A) {
+    constexpr unsigned W = 2u * NP, NH = NP / 2u;  // sites per strip, float4 per strip
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ int s_skip;
     // an earlier launch flagged an event: this one will be replayed.  ONE thread decides for the CTA -- the word may rise
@@ -89,7 +94,7 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
     unsigned bx;
     cta_slice_position(A, tl, bx);
     const bool edge_lo = A.slab_on && tl == 0, edge_hi = A.slab_on && tl == A.nt - 1;
-    // ---- geometry: thread (tx, ty) owns strip position x0 = 4 tx of rows r_start .. r_start + R - 1 ------------
+    // ---- geometry: thread (tx, ty) owns strip position x0 = W tx of rows r_start .. r_start + R - 1 ------------
     const unsigned L0 = L0T ? (unsigned)L0T : (unsigned)A.dim[0], L1 = (unsigned)A.dim[1];
     const unsigned L2 = (NDIM >= 4) ? (unsigned)A.dim[2] : 1u;
     const unsigned ROWB = L0 * 4u;  // bytes per row
@@ -130,13 +135,9 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
         }
     }
 
-    unsigned x1s = r_start, x2 = 0;
-    if (NDIM >= 4) {
-        x2 = r_start / L1;
-        x1s = r_start - x2 * L1;
-    }
-    (void)x1s;
-    const unsigned x0 = tx * 4u;
+    unsigned x2 = 0;
+    if (NDIM >= 4) x2 = r_start / L1;
+    const unsigned x0 = tx * W;
     const float *tm = (tl > 0) ? cur - vs : (A.wrap_time ? in + (long long)(A.nt - 1) * vs : (const float *)A.ghost_lo);
     const float *tp = (tl < A.nt - 1) ? cur + vs : (A.wrap_time ? in : (const float *)A.ghost_hi);
     float *dst = (float *)A.out + (long long)chain * A.chain_stride + (long long)tl * vs;
@@ -145,20 +146,20 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
     const unsigned o0 = r_start * L0 + x0;  // offset of the thread's first strip inside the slice (reals)
     unsigned o = o0;                        // (REBASE) offset of the strip in hand
     // per-thread stream bases (bytes); pass k adds k * ROWB
-    const char *p_tp = (const char *)(tp + o), *p_tm = (const char *)(tm + o);
+    const char *p_tp = (const char *)(tp + o0), *p_tm = (const char *)(tm + o0);
     const char *p_u2 = nullptr, *p_d2 = nullptr;
     if (NDIM >= 4) {
-        p_u2 = (const char *)(cur + o) + (long long)((x2 + 1 == L2) ? -(long long)(L2 - 1) * plane : (long long)plane) * 4;
-        p_d2 = (const char *)(cur + o) + (long long)((x2 == 0) ? (long long)(L2 - 1) * plane : -(long long)plane) * 4;
+        p_u2 = (const char *)(cur + o0) + (long long)((x2 + 1 == L2) ? -(long long)(L2 - 1) * plane : (long long)plane) * 4;
+        p_d2 = (const char *)(cur + o0) + (long long)((x2 == 0) ? (long long)(L2 - 1) * plane : -(long long)plane) * 4;
     }
-    char *p_dst = (char *)(dst + o);
+    char *p_dst = (char *)(dst + o0);
     // shared-memory addresses of the thread's first strip and its x0 neighbours
     const unsigned rt = ty * R;  // row inside the tile
     const unsigned sg_t = rt / seg_rows;
     const unsigned s_row = data0 + sg_t * seg_bytes + (1u + rt - sg_t * seg_rows) * ROWB;
     unsigned s_c = s_row + x0 * 4u;
     unsigned s_left = s_row + ((x0 == 0) ? (L0 - 1u) * 4u : x0 * 4u - 4u);
-    unsigned s_right = s_row + ((x0 + 4 == L0) ? 0u : x0 * 4u + 16u);
+    unsigned s_right = s_row + ((x0 + W == L0) ? 0u : (x0 + W) * 4u);
 
     // ---- chain state: T = seed before the thread's first draw + 2^31, per-row affine advance ------------------
     const u64 gslice = (u64)(A.slab_t0 + tl) * (u64)vs;
@@ -166,10 +167,10 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
     unsigned cnt_prev = 0, nxt32 = 0x7FFFFFFFu;
     u64 S_eff = S;
     if (REBASE) {
-        const Rebased rb = rebase_eval(A.rebase, A.n_rebase, chain, S, gslice + o, gslice, (unsigned)vs);
+        const Rebased rb = rebase_eval(A.rebase, A.n_rebase, chain, S, gslice + o0, gslice, (unsigned)vs, W);
         S_eff = rb.S_eff;
         cnt_prev = rb.cnt;
-        nxt32 = rb.slow ? o : rb.nxt32;  // an entry inside the first strip: take the rare path at k == 0
+        nxt32 = rb.slow ? o0 : rb.nxt32;  // an entry inside the first strip: take the rare path at k == 0
     }
     // three precomputed jumps from gid 0: slice start, CTA's first row, this thread's first strip
     unsigned Tl, Th;
@@ -184,12 +185,12 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
     }
     const unsigned aDl = (unsigned)A.row_jump.a, aDh = (unsigned)(A.row_jump.a >> 32);
     // T(next row) = alpha^L0 T + ck ; ck itself is a running sum
-    u64 ck = (LCG_BETA * (gslice + o) + LCG_GAMMA) * A.row_jump.g0 + A.row_jump.bg1 - A.row_jump.a * TWO31 + TWO31;
+    u64 ck = (LCG_BETA * (gslice + o0) + LCG_GAMMA) * A.row_jump.g0 + A.row_jump.bg1 - A.row_jump.a * TWO31 + TWO31;
     // site constants of the strip's first site: t1 = A T + c1, T' = A^2 T + c2 ; +A / +(A^2+A) per site
-    u64 c1 = site_const(gslice + o) - LCG_A * TWO31;
-    u64 c2 = (LCG_A + 1) * site_const(gslice + o) - LCG_ALPHA * TWO31;
-    // (the per-row increments A.t_dck, A.t_dc1 = (L0 - 3) A, A.t_dc2 = (L0 - 3)(A^2 + A) are kernel parameters: constant-bank
-    // operands of the adds, not registers)
+    u64 c1 = site_const(gslice + o0) - LCG_A * TWO31;
+    u64 c2 = (LCG_A + 1) * site_const(gslice + o0) - LCG_ALPHA * TWO31;
+    // (the per-row increments A.t_dck, A.t_dc1 = (L0 - (W-1)) A, A.t_dc2 = (L0 - (W-1))(A^2 + A) are kernel parameters:
+    // constant-bank operands of the adds, not registers)
 
     // ---- constants as fp32 pairs -------------------------------------------------------------------------
     const float c_lap = (float)A.c_lap, c_dt = (float)A.c_dt;
@@ -206,22 +207,26 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
     pair_t ACC1 = 0, ACC2 = 0;  // (+0.0f, +0.0f)
     unsigned nclamp = 0;
 
-    // ---- one pass = one strip of 4 sites; `kb` = byte offset of the pass inside the thread's streams --------
+    // ---- one pass = one strip of W sites; `kb` = byte offset of the pass inside the thread's streams, k its row ----
     auto pass = [&](const unsigned kb, const unsigned k) {
         // t+-1 and x2+-1 have no reuse: straight from global memory, requested now, used after the noise phase
-        ulonglong2 U2, D2;
-        if (NDIM >= 4) {
-            U2 = ldg128(p_u2 + kb);
-            D2 = ldg128(p_d2 + kb);
+        ulonglong2 U2[NH], D2[NH], TP[NH], TM[NH];
+#pragma unroll
+        for (unsigned h = 0; h < NH; ++h) {
+            if (NDIM >= 4) {
+                U2[h] = ldg128(p_u2 + kb + 16u * h);
+                D2[h] = ldg128(p_d2 + kb + 16u * h);
+            }
+            TP[h] = ldg128(p_tp + kb + 16u * h);
+            TM[h] = ldg128(p_tm + kb + 16u * h);
         }
-        const ulonglong2 TP = ldg128(p_tp + kb), TM = ldg128(p_tm + kb);
 
-        // ---- noise phase: 4 draws in t2 form, Box-Muller ------------------------------------------------
+        // ---- noise phase: W draws in t2 form, Box-Muller ------------------------------------------------
         const unsigned T0l = Tl, T0h = Th;
         unsigned tl_ = Tl, th_ = Th, um = 0xFFFFFFFFu;
-        pair_t NZ[2];
+        pair_t NZ[NP];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (unsigned q = 0; q < (unsigned)NP; ++q) {
             unsigned u1a, u2a, u1b, u2b, al, ah, bl, bh;
             mad48t(tl_, th_, A_LO, A_HI, c1, al, ah);
             mad48t(tl_, th_, ALPHA_LO32T, ALPHA_HI32T, c2, bl, bh);
@@ -233,7 +238,7 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
             mad48t(bl, bh, ALPHA_LO32T, ALPHA_HI32T, c2, tl_, th_);
             u1b = __funnelshift_r(al, ah, 16);
             u2b = __funnelshift_r(tl_, th_, 16);
-            if (q == 0) {
+            if (q + 1 < (unsigned)NP) {
                 c1 += LCG_A;
                 c2 += LCG_BETA;
             } else {  // on to the first site of the next row
@@ -260,64 +265,70 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
         }
 
         // ---- stencil phase ------------------------------------------------------------------------------------
-        const ulonglong2 C = lds128(s_c + kb), U1 = lds128(s_c + kb + ROWB), D1 = lds128(s_c + kb - ROWB);
+        pair_t C[NP], U1[NP], D1[NP];
+#pragma unroll
+        for (unsigned h = 0; h < NH; ++h) {
+            const ulonglong2 c = lds128(s_c + kb + 16u * h), u = lds128(s_c + kb + ROWB + 16u * h), d = lds128(s_c + kb - ROWB + 16u * h);
+            C[2 * h] = c.x; C[2 * h + 1] = c.y;
+            U1[2 * h] = u.x; U1[2 * h + 1] = u.y;
+            D1[2 * h] = d.x; D1[2 * h + 1] = d.y;
+        }
         const float left = lds32(s_left + kb), right = lds32(s_right + kb);
-        float c0, c1f, c2f, c3;
-        upk(C.x, c0, c1f);
-        upk(C.y, c2f, c3);
-        pair_t S01 = pk(__fadd_rn(c1f, left), __fadd_rn(c2f, c0));  // phi(+0) + phi(-0)
-        pair_t S23 = pk(__fadd_rn(c3, c1f), __fadd_rn(right, c2f));
-        S01 = add2(S01, U1.x);
-        S23 = add2(S23, U1.y);
-        S01 = add2(S01, D1.x);
-        S23 = add2(S23, D1.y);
-        if (NDIM >= 4) {
-            S01 = add2(S01, U2.x);
-            S23 = add2(S23, U2.y);
-            S01 = add2(S01, D2.x);
-            S23 = add2(S23, D2.y);
+        float p[W];
+#pragma unroll
+        for (unsigned q = 0; q < (unsigned)NP; ++q) upk(C[q], p[2 * q], p[2 * q + 1]);
+        pair_t V[NP];
+        float amax = 0.f;
+#pragma unroll
+        for (unsigned q = 0; q < (unsigned)NP; ++q) {
+            const float xm0 = (q == 0) ? left : p[(2 * q + W - 1) % W], xp1 = (q == (unsigned)NP - 1) ? right : p[(2 * q + 2) % W];
+            pair_t Sq = pk(__fadd_rn(p[2 * q + 1], xm0), __fadd_rn(xp1, p[2 * q]));  // phi(+0) + phi(-0)
+            Sq = add2(Sq, U1[q]);
+            Sq = add2(Sq, D1[q]);
+            if (NDIM >= 4) {
+                Sq = add2(Sq, (q & 1) ? U2[q / 2].y : U2[q / 2].x);
+                Sq = add2(Sq, (q & 1) ? D2[q / 2].y : D2[q / 2].x);
+            }
+            Sq = add2(Sq, (q & 1) ? TP[q / 2].y : TP[q / 2].x);
+            Sq = add2(Sq, (q & 1) ? TM[q / 2].y : TM[q / 2].x);
+            pair_t v = fma2(K_clap, fma2(K_m2d, C[q], Sq), C[q]);
+            if (POT == 4) v = fma2(K_mcdt, mul2(C[q], fma2(K_lam, mul2(C[q], C[q]), K_m2)), v);
+            else v = fma2(K_m2cdt, C[q], v);  // (-c_dt)(2 phi) == (-2 c_dt) phi exactly
+            v = fma2(K_m1, NZ[q], v);          // v + dw, one rounding
+            V[q] = v;
+            float a0, a1;
+            upk(v, a0, a1);
+            amax = fmaxf(fmaxf(fabsf(a0), fabsf(a1)), amax);
+            ACC1 = add2(ACC1, C[q]);           // observables of the pre-update field
+            ACC2 = fma2(C[q], C[q], ACC2);
         }
-        S01 = add2(S01, TP.x);
-        S23 = add2(S23, TP.y);
-        S01 = add2(S01, TM.x);
-        S23 = add2(S23, TM.y);
-        pair_t V01 = fma2(K_clap, fma2(K_m2d, C.x, S01), C.x);
-        pair_t V23 = fma2(K_clap, fma2(K_m2d, C.y, S23), C.y);
-        if (POT == 4) {
-            V01 = fma2(K_mcdt, mul2(C.x, fma2(K_lam, mul2(C.x, C.x), K_m2)), V01);
-            V23 = fma2(K_mcdt, mul2(C.y, fma2(K_lam, mul2(C.y, C.y), K_m2)), V23);
-        } else {
-            V01 = fma2(K_m2cdt, C.x, V01);  // (-c_dt)(2 phi) == (-2 c_dt) phi exactly
-            V23 = fma2(K_m2cdt, C.y, V23);
-        }
-        V01 = fma2(K_m1, NZ[0], V01);  // v + dw, one rounding
-        V23 = fma2(K_m1, NZ[1], V23);
-        // clamp (tau_kernel.cl:122-132): values at or beyond +-1000 leave through one test per strip
-        float v0, v1, v2, v3;
-        upk(V01, v0, v1);
-        upk(V23, v2, v3);
-        const float amax = fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3)));
-        if (__builtin_expect(!(amax < 1000.0f) | (um < 32768u), 0)) {  // one test per strip for both rare cases
+        // clamp (tau_kernel.cl:122-132) and RNG events: one test per strip for both rare cases
+        if (__builtin_expect(!(amax < 1000.0f) | (um < 32768u), 0)) {
             bool replayed = false;  // an event in this strip: the launch is redone, its clamp hits are not counted
             if (um < 32768u) {
                 const u64 z0 = ((((u64)T0h << 32) | T0l) - TWO31) & LCG_MASK;
-                replayed = strip_events_cold(A.event_key, A.step_index, chain, z0, (u64)(A.slab_t0 + tl) * (u64)A.vslice + o0 + k * L0, 4);
+                replayed = strip_events_cold(A.event_key, A.step_index, chain, z0, (u64)(A.slab_t0 + tl) * (u64)A.vslice + o0 + k * L0, (int)W);
             }
-            const Clamped cl = clamp_cold(v0, v1, v2, v3);
-            V01 = pk(cl.v[0], cl.v[1]);
-            V23 = pk(cl.v[2], cl.v[3]);
-            if (!replayed) nclamp += cl.n;
+#pragma unroll
+            for (unsigned h = 0; h < NH; ++h) {
+                float v0, v1, v2, v3;
+                upk(V[2 * h], v0, v1);
+                upk(V[2 * h + 1], v2, v3);
+                const Clamped cl = clamp_cold(v0, v1, v2, v3);
+                V[2 * h] = pk(cl.v[0], cl.v[1]);
+                V[2 * h + 1] = pk(cl.v[2], cl.v[3]);
+                if (!replayed) nclamp += cl.n;
+            }
         }
-        // ---- observables of the pre-update field, store ------------------------------------------------------
-        ACC1 = add2(ACC1, C.x);
-        ACC1 = add2(ACC1, C.y);
-        ACC2 = fma2(C.x, C.x, ACC2);
-        ACC2 = fma2(C.y, C.y, ACC2);
-        *reinterpret_cast<ulonglong2 *>(p_dst + kb) = make_ulonglong2(V01, V23);
+#pragma unroll
+        for (unsigned h = 0; h < NH; ++h) *reinterpret_cast<ulonglong2 *>(p_dst + kb + 16u * h) = make_ulonglong2(V[2 * h], V[2 * h + 1]);
         if (__builtin_expect(push_lo | push_hi, 0)) {  // CTA-uniform: boundary slices of a slab ring only
             const size_t oo = (size_t)(o0 + k * L0) * 4u;
-            if (push_lo) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[0] + oo) = make_ulonglong2(V01, V23);
-            if (push_hi) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[1] + oo) = make_ulonglong2(V01, V23);
+#pragma unroll
+            for (unsigned h = 0; h < NH; ++h) {
+                if (push_lo) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[0] + oo + 16u * h) = make_ulonglong2(V[2 * h], V[2 * h + 1]);
+                if (push_hi) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[1] + oo + 16u * h) = make_ulonglong2(V[2 * h], V[2 * h + 1]);
+            }
         }
     };
 
@@ -326,7 +337,7 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
         const unsigned x1 = ((NDIM >= 4) ? (r_start - x2 * L1) : r_start) + k;
         const u64 gsl = (u64)(A.slab_t0 + tl) * (u64)A.vslice;
         const u64 g0 = gsl + o;
-        const Rebased rb = rebase_eval(A.rebase, A.n_rebase, chain, A.seed_in[chain], g0, gsl, (unsigned)A.vslice);
+        const Rebased rb = rebase_eval(A.rebase, A.n_rebase, chain, A.seed_in[chain], g0, gsl, (unsigned)A.vslice, W);
         nxt32 = rb.nxt32;
         if (rb.cnt != cnt_prev) {  // new base: the thread's first strip under the new start seed, k rows down
             cnt_prev = rb.cnt;
@@ -343,28 +354,35 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
             Th = (unsigned)(t >> 32);
         }
         if (!rb.slow) return false;
-        // the whole strip out of line; the row recurrence is void behind an entry (re-evaluated at the next strip)
+        // the whole strip out of line, four sites at a time; the row recurrence is void behind an entry (re-evaluated at
+        // the next strip)
         const unsigned row_wrap = (L1 - 1) * L0;
-        SlowIn I;
-        I.cur = cur; I.tm = tm; I.tp = tp; I.dst = dst;
-        I.push0 = push_lo ? (float *)A.push_ghost[0] : nullptr;
-        I.push1 = push_hi ? (float *)A.push_ghost[1] : nullptr;
-        I.o = o;
-        I.o_up1 = o + ((x1 + 1 == L1) ? 0u - row_wrap : L0);
-        I.o_dn1 = o + ((x1 == 0) ? row_wrap : 0u - L0);
-        I.o_up2 = (NDIM >= 4) ? o + ((x2 + 1 == L2) ? 0u - (L2 - 1) * plane : plane) : 0u;
-        I.o_dn2 = (NDIM >= 4) ? o + ((x2 == 0) ? (L2 - 1) * plane : 0u - plane) : 0u;
-        I.o_left = o + ((x0 == 0) ? L0 - 1u : 0u - 1u);
-        I.o_right = o + ((x0 + 4 == L0) ? 4u - L0 : 4u);
-        I.s = ((((u64)Th << 32) | Tl) - TWO31) & LCG_MASK;
-        I.g0 = g0;
-        I.chain = chain; I.step_index = A.step_index; I.n_rebase = A.n_rebase;
-        I.rebase = A.rebase; I.event_key = A.event_key;
-        I.c_lap = c_lap; I.c_dt = c_dt; I.m2 = m2; I.lam = lam; I.k2 = A.k2_f; I.nscale = A.nscale;
-        const SlowOut so = strip_slow<MATH, NDIM, POT>(I);
-        ACC1 = add2(ACC1, pk(so.a1, 0.f));
-        ACC2 = add2(ACC2, pk(so.a2, 0.f));
-        nclamp += so.nclamp;
+        u64 sq = ((((u64)Th << 32) | Tl) - TWO31) & LCG_MASK;
+#pragma unroll 1
+        for (unsigned h = 0; h < NH; ++h) {
+            const unsigned oh = o + 4u * h, xh = x0 + 4u * h;
+            SlowIn I;
+            I.cur = cur; I.tm = tm; I.tp = tp; I.dst = dst;
+            I.push0 = push_lo ? (float *)A.push_ghost[0] : nullptr;
+            I.push1 = push_hi ? (float *)A.push_ghost[1] : nullptr;
+            I.o = oh;
+            I.o_up1 = oh + ((x1 + 1 == L1) ? 0u - row_wrap : L0);
+            I.o_dn1 = oh + ((x1 == 0) ? row_wrap : 0u - L0);
+            I.o_up2 = (NDIM >= 4) ? oh + ((x2 + 1 == L2) ? 0u - (L2 - 1) * plane : plane) : 0u;
+            I.o_dn2 = (NDIM >= 4) ? oh + ((x2 == 0) ? (L2 - 1) * plane : 0u - plane) : 0u;
+            I.o_left = oh + ((xh == 0) ? L0 - 1u : 0u - 1u);
+            I.o_right = oh + ((xh + 4 == L0) ? 4u - L0 : 4u);
+            I.s = sq;
+            I.g0 = g0 + 4u * h;
+            I.chain = chain; I.step_index = A.step_index; I.n_rebase = A.n_rebase;
+            I.rebase = A.rebase; I.event_key = A.event_key;
+            I.c_lap = c_lap; I.c_dt = c_dt; I.m2 = m2; I.lam = lam; I.k2 = A.k2_f; I.nscale = A.nscale;
+            const SlowOut so = strip_slow<MATH, NDIM, POT>(I);
+            ACC1 = add2(ACC1, pk(so.a1, 0.f));
+            ACC2 = add2(ACC2, pk(so.a2, 0.f));
+            nclamp += so.nclamp;
+            sq = so.s_after;
+        }
         nxt32 = o + L0;  // re-evaluate at the next strip (new base)
         ck += A.t_dck;
         c1 += (u64)L0 * LCG_A;
@@ -375,7 +393,7 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
     tile_mbar_wait(bar, 0);  // the tile has landed (other CTAs of the SM computed meanwhile)
     // ---- the thread's R strips: U passes per trip (pass offsets are immediates), then the stream bases move on --------
     // (R is a multiple of 4 -- tile_shape_ok -- so the event-free instance needs no tail test)
-    constexpr unsigned U = REBASE ? 1u : 4u;
+    constexpr unsigned U = REBASE ? 1u : (NP == 4 ? 2u : 4u);
     for (unsigned k0 = 0; k0 < R; k0 += U) {
 #pragma unroll
         for (unsigned u = 0; u < U; ++u) {
@@ -384,7 +402,7 @@ __global__ void __launch_bounds__(256, REBASE ? 3 : TILE_MINB) lattice_tile_kern
             bool done = false;
             if (REBASE) {
                 o = o0 + (k0 + u) * L0;
-                if (__builtin_expect((int)(nxt32 - o) <= 4, 0)) done = slow_strip(k0 + u);
+                if (__builtin_expect((int)(nxt32 - o) <= (int)W, 0)) done = slow_strip(k0 + u);
             }
             if (!done) pass(u * ROWB, k0 + u);
         }
@@ -474,23 +492,25 @@ size_t tile_smem_bytes(int L0, int L1, int tpr_log, int R) {
     const unsigned seg_rows = rows_per_cta < (unsigned)L1 ? rows_per_cta : (unsigned)L1, nseg = rows_per_cta / seg_rows;
     return 128 + (size_t)nseg * (seg_rows + 2u) * (size_t)L0 * 4u;
 }
-// the tile must be a whole number of planes or divide one (runs of rows never straddle a plane edge)
+// the tile must be a whole number of planes or divide one (runs of rows never straddle a plane edge); tpr_log = log2 of the
+// threads per row (row length / sites per strip)
 bool tile_shape_ok(int L0, int L1, int tpr_log, int R) {
     const unsigned rows_per_cta = (256u >> tpr_log) * (unsigned)R;
     if (L1 % R != 0 || R % 4 != 0) return false;
     if (!(rows_per_cta % (unsigned)L1 == 0 || (unsigned)L1 % rows_per_cta == 0)) return false;
-    return tile_smem_bytes(L0, L1, tpr_log, R) <= 72 * 1024;  // three CTAs per SM (the register budget allows no more)
+    return tile_smem_bytes(L0, L1, tpr_log, R) <= 72 * 1024;
 }
 
+// Instantiated: 4-site strips, event-free steps.  (8-site strips -- 124 registers, two CTAs per SM -- were measured at
+// 328 G site-updates/s on 256^3 slices against 368 for 4-site strips; steps with replay entries go to the marching kernel,
+// which shares this kernel's tiles and jump tables.)
 template <int MATH, int NDIM, int POT, int L0T>
 static cudaError_t tile_go(const LatticeArgs &A, dim3 grid, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024) {  // (idempotent; the attribute is per function)
-        cudaError_t e = cudaFuncSetAttribute(lattice_tile_kernel<MATH, NDIM, POT, L0T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(lattice_tile_kernel<MATH, NDIM, POT, L0T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(lattice_tile_kernel<MATH, NDIM, POT, L0T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
         if (e != cudaSuccess) return e;
     }
-    if (A.n_rebase > 0) lattice_tile_kernel<MATH, NDIM, POT, L0T, true><<<grid, 256, smem, st>>>(A);
-    else lattice_tile_kernel<MATH, NDIM, POT, L0T, false><<<grid, 256, smem, st>>>(A);
+    lattice_tile_kernel<MATH, NDIM, POT, L0T, 2, false><<<grid, 256, smem, st>>>(A);
     return cudaGetLastError();
 }
 template <int MATH, int NDIM, int POT>
@@ -510,6 +530,7 @@ static cudaError_t tile_pot(const LatticeArgs &A, dim3 grid, size_t smem, cudaSt
 cudaError_t launch_lattice_tile(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream) {
     dim3 grid((unsigned)ctas_per_slice, (unsigned)A.nt, (unsigned)A.nchains);
     const size_t smem = tile_smem_bytes((int)A.dim[0], (int)A.dim[1], A.m_tpr_log, A.m_R);
+    if (A.m_w != 4 || A.n_rebase != 0) return cudaErrorInvalidValue;
     if (A.ndim == 3) return math ? tile_pot<1, 3>(A, grid, smem, stream) : tile_pot<0, 3>(A, grid, smem, stream);
     if (A.ndim == 4) return math ? tile_pot<1, 4>(A, grid, smem, stream) : tile_pot<0, 4>(A, grid, smem, stream);
     return cudaErrorInvalidValue;
