@@ -140,21 +140,28 @@ __device__ __noinline__ Pair2 clamp4_cold(pair_t a, pair_t b) {
     return r;
 }
 
-// reducer warps when a CTA has fewer warps than (row, kind) items (small lattices): the general walk
-__device__ __noinline__ void reduce_rows_general(double *hist_rows, double *hist_p2, int L1, unsigned rs_par, unsigned rsk, int TPR,
-                                                 int first, int nw, int nr, int r0, int step, int lane) {
-    for (int it = first; it < 2 * nr; it += nw) {
-        const int row = it >> 1, kind = it & 1;
-        const unsigned src = rs_par + (unsigned)kind * rsk + (unsigned)(row * TPR) * 4u;
-        float a = 0.f;
-        for (int i = 4 * lane; i < TPR; i += 128) {
+// reducer warps when a CTA has fewer warps than rows (small lattices): the general walk.  rs_par: the parity's array of
+// {sum phi, sum phi^2} pairs, one per thread.
+__device__ __noinline__ void reduce_rows_general(double *hist_rows, double *hist_p2, int L1, unsigned rs_par, int TPR, int first, int nw,
+                                                 int nr, int r0, int step, int lane) {
+    for (int row = first; row < nr; row += nw) {
+        const unsigned src = rs_par + (unsigned)(row * TPR) * 8u;
+        float a = 0.f, q = 0.f;
+        for (int i = 2 * lane; i < TPR; i += 64) {
             float4 v;
-            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + (unsigned)i * 4u));
-            a += (v.x + v.y) + (v.z + v.w);
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(src + (unsigned)i * 8u));
+            a += v.x + v.z;
+            q += v.y + v.w;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) (kind ? hist_p2 : hist_rows)[(size_t)step * L1 + r0 + row] = (double)a;
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (lane == 0) {
+            hist_rows[(size_t)step * L1 + r0 + row] = (double)a;
+            hist_p2[(size_t)step * L1 + r0 + row] = (double)q;
+        }
     }
 }
 
@@ -169,7 +176,7 @@ __device__ __noinline__ void checkpoint4_cold(float *dst, pair_t a, pair_t b) {
 // step loop is instantiated per role -- a plain warp's loop carries no halo, reduction or service code:
 //   EDGE     0 interior row | 1 first row of the band | 2 last row (a band has at least two rows): the edge rows
 //            talk to the neighbour CTAs through the halo words
-//   REDUCER  one warp per (row, kind) turns the row-sum partials into the per-step history; the first of them also
+//   REDUCER  one warp per row turns the row's {sum phi, sum phi^2} partials into the per-step history; the first of them also
 //            polls the event word and (CTA 0) draws for the omega work-item
 constexpr int RES_MAX_STEPS_K = 2048;  // = RES_MAX_STEPS (sq_ctx.h): hist_p2 = hist_rows + RES_MAX_STEPS_K * L1
 constexpr int ROWRES_THREADS = 896;  // 7 rows x 128 strips for 1024^2; 72 registers per thread
@@ -194,9 +201,9 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
     const int jl = (j == 0) ? TPR - 1 : j - 1, jr = (j + 1 == TPR) ? 0 : j + 1;
     const unsigned d_left = (unsigned)(((NH - 1) * TPR + jl) * 16 + 12) - (unsigned)j * 16u;  // relative to a_own (wraps mod 2^32)
     const unsigned d_right = (unsigned)jr * 16u - (unsigned)j * 16u;
-    const unsigned rs_base = G.smem_base + 2u * parb;                   // rs[2 parity][2 kind][NRM][TPR] floats
-    const unsigned rsk = (unsigned)(NRM * TPR) * 4u;                    // bytes between the two kinds
-    const unsigned a_rs = rs_base + (unsigned)(k * TPR + j) * 4u;
+    const unsigned rs_base = G.smem_base + 2u * parb;                   // rs[2 parity][NRM][TPR] pairs {sum phi, sum phi^2}
+    const unsigned rsp = (unsigned)(NRM * TPR) * 8u;                    // bytes between the two parities
+    const unsigned a_rs = rs_base + (unsigned)(k * TPR + j) * 8u;
     const unsigned a_chain = G.chain_a + (unsigned)tid * 16u;           // {T, K2} ; + 16 blockDim: {c1_0, c2_0} ; + 32 blockDim: role slot
     const unsigned chain_pl = (unsigned)blockDim.x * 16u;
 
@@ -265,33 +272,41 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
     };
 
     // ---- reducer duties ------------------------------------------------------------------------------
-    // A reducer warp's first item is (row = wid / 2, kind = wid % 2).  What it needs every step -- its shared-memory
-    // source (parity 0), the word offset of its history entry, the mask of lanes beyond the row (a lane covers 4
-    // partials per 128 threads of the row) -- sits in the thread's role slot in shared memory: registers are what this
-    // loop is short of, and ptxas would otherwise re-derive all of it from %tid every step.
+    // A reducer warp reduces ONE row per step (warp w: row w; fewer warps than rows: the general walk): the row's TPR
+    // pairs {sum phi, sum phi^2} -> two history entries.  A lane covers 4 pairs per 128 threads of the row (TPR <= 256).
+    // What it needs every step -- its shared-memory source (parity 0), the word offset of its history entries, the mask of
+    // lanes beyond the row -- sits in the thread's role slot in shared memory: registers are what this loop is short of,
+    // and ptxas would otherwise re-derive all of it from %tid every step.
     const int nw = (nr * TPR) >> 5;
     if (REDUCER) {
         const int wid = tid >> 5;
         const bool red_lane = 4 * lane < TPR;
-        const unsigned red_src = rs_base + (unsigned)(wid & 1) * rsk + (unsigned)((wid >> 1) * TPR + (red_lane ? 4 * lane : 0)) * 4u;
-        const unsigned red_off = (unsigned)(wid & 1) * (unsigned)RES_MAX_STEPS_K * (unsigned)A.L1 + (unsigned)(r0 + (wid >> 1));
+        const unsigned red_src = rs_base + (unsigned)(wid * TPR + (red_lane ? 4 * lane : 0)) * 8u;
+        const unsigned red_off = (unsigned)(r0 + wid);
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_chain + 2u * chain_pl), "r"(red_src), "r"(red_off),
                      "r"(__float_as_uint(red_lane ? 1.0f : 0.0f)), "r"((unsigned)wid + (unsigned)nw) : "memory");
     }
     auto reduce_rows = [&](int step, unsigned parity) {
         unsigned red_src, red_off, red_mask, red_next;
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(red_src), "=r"(red_off), "=r"(red_mask), "=r"(red_next) : "r"(a_chain + 2u * chain_pl));
-        const float4 v = lds_f4(red_src + parity * 2u * rsk);
-        float a = ((v.x + v.y) + (v.z + v.w)) * __uint_as_float(red_mask);
+        const ulonglong2 v0 = lds_pairs(red_src + parity * rsp), v1 = lds_pairs(red_src + parity * rsp + 16u);
+        const pair_t M = pk(__uint_as_float(red_mask), __uint_as_float(red_mask));
+        pair_t acc = mul2(add2(add2(v0.x, v0.y), add2(v1.x, v1.y)), M);  // {sum phi, sum phi^2} of 4 threads
         if (TPR > 128) {  // (uniform) rows of more than 128 strips: a second chunk per lane
-            const float4 w = lds_f4(red_src + parity * 2u * rsk + 512u);
-            a += (4 * lane + 128 < TPR) ? (w.x + w.y) + (w.z + w.w) : 0.f;
+            const ulonglong2 w0 = lds_pairs(red_src + parity * rsp + 1024u), w1 = lds_pairs(red_src + parity * rsp + 1040u);
+            if (4 * lane + 128 < TPR) acc = add2(acc, add2(add2(w0.x, w0.y), add2(w1.x, w1.y)));
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) A.hist_rows[red_off + (unsigned)step * (unsigned)A.L1] = (double)a;  // (hist_p2 follows hist_rows)
-        if (nw < 2 * nr)  // (uniform) fewer warps than items: the general walk
-            reduce_rows_general(A.hist_rows, A.hist_p2, A.L1, rs_base + parity * 2u * rsk, rsk, TPR, (int)red_next, nw, nr, r0, step, lane);
+        for (int o = 16; o > 0; o >>= 1) acc = add2(acc, (pair_t)__shfl_xor_sync(0xffffffffu, (unsigned long long)acc, o));
+        if (lane == 0) {
+            float a, q;
+            upk(acc, a, q);
+            const unsigned idx = red_off + (unsigned)step * (unsigned)A.L1;
+            A.hist_rows[idx] = (double)a;
+            A.hist_p2[idx] = (double)q;
+        }
+        if (nw < nr)  // (uniform) fewer warps than rows
+            reduce_rows_general(A.hist_rows, A.hist_p2, A.L1, rs_base + parity * rsp, TPR, (int)red_next, nw, nr, r0, step, lane);
     };
     // service lane (first reducer warp): event-word poll; CTA 0: the omega work-item's draws, whose running
     // step-start seed lives in shared memory too.
@@ -409,9 +424,7 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
             float sl, sh, pl, ph;
             upk(s, sl, sh);
             upk(p2, pl, ph);
-            const unsigned dst = a_rs + par * 2u * rsk;
-            sts_f32(dst, __fadd_rn(sl, sh));
-            sts_f32(dst + rsk, __fadd_rn(pl, ph));
+            sts_u64(a_rs + par * rsp, pk(__fadd_rn(sl, sh), __fadd_rn(pl, ph)));
         }
         // ---- update: s = phi(+0) + phi(-0); s += phi(+1); s += phi(-1)   -----------------
         float p[W];
@@ -548,7 +561,7 @@ __global__ void __launch_bounds__(ROWRES_THREADS, 1) rowres_kernel(const Residen
         sts_pairs(G.chain_a + (unsigned)(blockDim.x + tid) * 16u, c1_0, c2_0);
     }
     const int edge = (G.k == 0) ? 1 : ((G.k == G.nr - 1) ? 2 : 0);
-    const bool reducer = (tid >> 5) < 2 * G.nr;
+    const bool reducer = (tid >> 5) < G.nr;
 #define SQ_ROLE(E, R) rowres_steps<MATH, POT, NP, E, R>(A, PH, G)
     if (edge == 0) { if (reducer) SQ_ROLE(0, true); else SQ_ROLE(0, false); }
     else if (edge == 1) { if (reducer) SQ_ROLE(1, true); else SQ_ROLE(1, false); }
