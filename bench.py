@@ -340,7 +340,10 @@ def kernel_name(dims, real):
         resident = (dims[0] % 256 == 0 and rows * (dims[0] // 8) <= 896) or rows * (dims[0] // 4) <= 896
     if resident:
         return "rowres_kernel", True
-    return ("lattice_march_kernel" if len(dims) >= 3 and real == "f32" else "lattice_step_kernel"), False
+    if len(dims) >= 3 and real == "f32":
+        # bulk-copy staged tiles for event-free steps (the timed launches), the marching kernel where a step carries replay entries
+        return "lattice_tile_kernel", False
+    return "lattice_step_kernel", False
 
 
 def roofline_of(name, wl, ctx, kms, kn, loops):
@@ -354,9 +357,10 @@ def roofline_of(name, wl, ctx, kms, kn, loops):
     if os.path.exists(tp):
         try:
             t = json.load(open(tp)).get(name)
-            # ncu capture of one launch, scaled to the tau-steps one launch covers in this run
-            traffic = t["bytes_per_launch"] * (units_per_launch / Vloc / t["tau_steps_per_launch"])
-            tnote = t["source"]
+            # ncu capture of one launch of this workload's kernel covering the same number of tau-steps
+            if abs(units_per_launch / Vloc - t["tau_steps_per_launch"]) < 1e-9:
+                traffic = t["bytes_per_launch"]
+                tnote = t["source"]
         except Exception:
             traffic = None
     kname, resident = kernel_name(wl["dims"], wl["real"])

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(256, REBASE ? MARCH_MINB_RB : MARCH_MINB) latt
             upk(fma2(F2a, K_th, K_mpi), th[0], th[1]);
             upk(fma2(F2b, K_th, K_mpi), th[2], th[3]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = __fmaf_rn(-__cosf(th[e]), sqrt_approx(fabsf(t[e])), v[e]);
+            // dw = -RN(cos(theta - pi) rad), then v + dw: the two roundings every lattice kernel uses
+            for (int e = 0; e < 4; ++e) v[e] = __fsub_rn(v[e], __fmul_rn(__cosf(th[e]), sqrt_approx(fabsf(t[e]))));
         } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)

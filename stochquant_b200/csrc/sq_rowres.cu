@@ -109,6 +109,13 @@ __device__ __forceinline__ float4 lds_f4(unsigned a) {
     return v;
 }
 
+// ACCURATE noise out of line: eight inlined copies of logf / cosf / sqrtf and the fp64 products per role loop made the
+// kernel 12 k instructions (twice the FAST instance) -- no longer resident in the instruction caches (84 G site-updates/s
+// against 179 for the round-1 kernel); one shared copy restores it.
+__device__ __noinline__ float noise_accurate_dw(unsigned u1, unsigned u2, double nscale) {
+    return (float)__dmul_rn(nscale, noise_accurate((u64)u1 << 16, (u64)u2 << 16));
+}
+
 // cold: exact event test of the w draws of a strip from its start seed (literal replay is the host's job)
 __device__ __noinline__ void stripw_events_cold(u64 *event_key_ptr, int step, u64 sm, u64 g0, int w) {
     for (int e = 0; e < w; ++e) {
@@ -257,8 +264,7 @@ __device__ __forceinline__ void rowres_steps(const ResidentArgs &A, pair_t (&PH)
                 upk(fma2(pk(__uint2float_rn(u2a), __uint2float_rn(u2b)), K_th, K_mpi), tha, thb);
                 NZ[q] = mul2(pk(__cosf(tha), __cosf(thb)), pk(sqrt_approx(fabsf(ta)), sqrt_approx(fabsf(tb))));
             } else {
-                const float da = (float)__dmul_rn(A.nscale, noise_accurate((u64)u1a << 16, (u64)u2a << 16));
-                const float db = (float)__dmul_rn(A.nscale, noise_accurate((u64)u1b << 16, (u64)u2b << 16));
+                const float da = noise_accurate_dw(u1a, u2a, A.nscale), db = noise_accurate_dw(u1b, u2b, A.nscale);
                 NZ[q] = pk(-da, -db);
             }
         }

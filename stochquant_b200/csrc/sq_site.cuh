@@ -84,20 +84,20 @@ __device__ __forceinline__ u64 site_const(u64 gid) { return gid * LCG_A + LCG_B;
 //   `seed+=`    => t2 < 2^31 <=> u2 < 2^15
 __device__ __forceinline__ bool site_maybe_event(unsigned u1, unsigned u2) { return (u1 == 0u) | (u2 < 32768u); }
 
-// FAST noise amplitude: returns r * scale where r = cos(2*3.1415 v2) sqrt(-2 ln v1) and
-// k2 = 2 ln2 * scale^2 (scale folded under the square root).
-//   v1: exact RN conversion on the conversion unit (I2F), scaled by 2^-32 (exact)
-//   v2: top 23 bits of u2 through the exponent trick (ALU), |d theta| <= 7.5e-7
+// FAST noise, scalar form of what the packed kernels compute (sq_rowres.cu, sq_tile.cu, sq_march.cu) -- the SAME operations
+// and roundings, so a FAST fp32 run does not depend on which kernel took which step:
+//   v1 = (float)u1 * 2^-32 (exact scaling of the RN conversion), lg = lg2.approx(v1), rad = sqrt.approx(|lg * k2|)
+//   (k2 = 2 ln2 * scale^2: the amplitude folded under the square root), theta - pi = fma((float)u2, 2*3.1415*2^-32, -pi),
+//   dw = -RN(cos.approx(theta - pi) * rad)          [cos(theta) = -cos(theta - pi) keeps MUFU.COS in [-pi, pi)]
+// The caller adds dw with one more rounding.
 __device__ __forceinline__ float site_noise_fast(unsigned u1, unsigned u2, float k2) {
-    const float v1 = __uint2float_rn(u1) * 2.3283064365386963e-10f;
+    const float v1 = __fmul_rn(__uint2float_rn(u1), 2.3283064365386963e-10f);
     float lg;                                           // MUFU.LG2 (v1 >= 2^-32: never denormal)
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(v1));
     float rad;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(fabsf(lg * k2)));
-    const float f = __uint_as_float(0x3F800000u | (u2 >> 9));  // [1,2): 1 + v2 (23 bits)
-    // theta - pi = 2*3.1415*(f-1) - pi
-    const float th = __fmaf_rn(f, 6.283f, -6.283f - 3.14159265358979f);
-    return -__cosf(th) * rad;                           // cos(theta) = -cos(theta - pi)
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(fabsf(__fmul_rn(lg, k2))));
+    const float th = __fmaf_rn(__uint2float_rn(u2), (float)(2.0 * 3.1415 / 4294967296.0), -3.14159265358979f);
+    return -__fmul_rn(__cosf(th), rad);
 }
 
 }  // namespace sq

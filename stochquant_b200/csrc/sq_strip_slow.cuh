@@ -101,7 +101,7 @@ __device__ __noinline__ SlowOut strip_slow(const SlowIn I) {
             const float a = __fmul_rn(__uint2float_rn(d.u1[e]), 2.3283064365386963e-10f);
             const float t = __fmul_rn(lg2_approx(a), I.k2);
             const float th = __fmaf_rn(__uint2float_rn(d.u2[e]), kth, -3.14159265358979f);
-            v = __fmaf_rn(-__cosf(th), sqrt_approx(fabsf(t)), v);
+            v = __fsub_rn(v, __fmul_rn(__cosf(th), sqrt_approx(fabsf(t))));  // dw = -RN(cos rad), then v + dw
         } else {
             v = __fadd_rn(v, (float)__dmul_rn(I.nscale, noise_accurate((u64)d.u1[e] << 16, (u64)d.u2[e] << 16)));
         }

@@ -440,3 +440,25 @@ def test_free_field_ensemble_4d_marching_kernel(gpu_sq):
     bins = vals.reshape(20, -1).mean(axis=1)  # binned error (autocorrelation)
     err = bins.std(ddof=1) / np.sqrt(len(bins))
     assert abs(vals.mean() - want) < 5 * err + 1e-3 * want, (vals.mean(), want, err)
+
+
+@pytest.mark.parametrize("dims,flag", [((256, 96), 2), ((32, 8, 8, 8), 4), ((64, 16, 16), 4)])
+def test_fast_math_is_one_definition_across_kernels(gpu_sq, oracle, dims, flag):
+    """SQ_MATH_FAST is the same sequence of operations and roundings in every fp32 lattice kernel (sq_site.cuh:
+    site_noise_fast is the scalar form of the packed pipelines), so a run does not depend on which kernel took which
+    step: the on-chip kernel / the tile + marching kernels against the generic streaming kernel (SQ_FLAG_FORCE_STREAMING /
+    SQ_FLAG_GENERIC_KERNEL), bit for bit -- also across an RNG event, where the replayed step changes kernels."""
+    V = int(np.prod(dims))
+    rng = np.random.default_rng(31)
+    phi0 = (rng.normal(size=V) * 0.5).astype(np.float32)
+    for seed in (1242608872, seed_with_retry_at(oracle, V // 2 + 3)):
+        a = gpu_sq.Context(dims, real="f32", math="fast", potential=4, m2=0.25, lam=0.5, seed=seed)
+        b = gpu_sq.Context(dims, real="f32", math="fast", potential=4, m2=0.25, lam=0.5, seed=seed, flags=flag)
+        a.upload(phi0)
+        b.upload(phi0)
+        a.step(DTAU, 11)
+        b.step(DTAU, 11)
+        assert a.measure()["seed"] == b.measure()["seed"]
+        assert np.array_equal(a.download(), b.download())
+        a.close()
+        b.close()
