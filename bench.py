@@ -442,25 +442,41 @@ def ring_parity(sq, np, torch, dist, world, rank, local):
     return verdict
 
 
+NVLINK_STATUS = {"source": None, "why": None}
+
+
 def nvlink_bytes(local):
-    """NVLink data bytes (tx, rx) of this rank's GPU since driver load, summed over its links (NVML field values, KiB
-    counters); None where the driver does not report them."""
+    """NVLink data bytes (tx, rx) of this rank's GPU since driver load, summed over its links: NVML field values
+    (KiB counters), else `nvidia-smi nvlink -gt d`; None where neither reports them (NVLINK_STATUS says why)."""
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+    why = []
     try:
         import pynvml
         pynvml.nvmlInit()
-        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        phys = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
         h = pynvml.nvmlDeviceGetHandleByIndex(phys)
         ids = [pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX]
         vals = pynvml.nvmlDeviceGetFieldValues(h, ids)
-        out = []
-        for v in vals:
-            if v.nvmlReturn != 0:
-                return None
-            out.append(int(v.value.ullVal) * 1024)
-        return out
-    except Exception:
-        return None
+        if all(v.nvmlReturn == 0 for v in vals):
+            NVLINK_STATUS.update(source="nvml field values", why=None)
+            return [int(v.value.ullVal) * 1024 for v in vals]
+        why.append("nvml field values: nvmlReturn %s" % [int(v.nvmlReturn) for v in vals])
+    except Exception as e:  # noqa: BLE001
+        why.append("nvml: %s: %s" % (type(e).__name__, e))
+    try:
+        import re
+        import subprocess
+        txt = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(phys)], capture_output=True, text=True, timeout=20).stdout
+        tx = [int(m) for m in re.findall(r"Data Tx:\s*(\d+)\s*KiB", txt)]
+        rx = [int(m) for m in re.findall(r"Data Rx:\s*(\d+)\s*KiB", txt)]
+        if tx and rx:
+            NVLINK_STATUS.update(source="nvidia-smi nvlink -gt d", why=None)
+            return [sum(tx) * 1024, sum(rx) * 1024]
+        why.append("nvidia-smi nvlink -gt d: no counters in %r" % txt[:120])
+    except Exception as e:  # noqa: BLE001
+        why.append("nvidia-smi: %s: %s" % (type(e).__name__, e))
+    NVLINK_STATUS.update(source=None, why="; ".join(why))
+    return None
 
 
 def ring_block(sq, np, torch, dist, timer, world, rank, local, args):
@@ -510,7 +526,8 @@ def ring_block(sq, np, torch, dist, timer, world, rank, local, args):
                # NVML's NVLink data counters of rank 0's GPU around the timed frames (includes the L2 flushes' nothing: the
                # flush is local) -- the halo slices are the only peer traffic of the run
                "nvlink_bytes_per_tau_step_rank0": ({"tx": (nv1[0] - nv0[0]) / (steps * loops), "rx": (nv1[1] - nv0[1]) / (steps * loops),
-                                                    "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX field values"} if nv0 and nv1 else None),
+                                                    "source": NVLINK_STATUS["source"]} if nv0 and nv1 else None),
+               "nvlink_counters_unavailable": (None if nv0 and nv1 else NVLINK_STATUS["why"]),
                "finder_scans_per_tau_step": stats["finder_scans"] / nsteps_total,
                "agree_rounds_per_tau_step": stats["agree_rounds"] / nsteps_total,
                "ring_parity": parity,

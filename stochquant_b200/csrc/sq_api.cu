@@ -105,7 +105,7 @@ extern "C" void sq_free(sq_ctx *c) {
                     c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps, c->c_ctl, c->c_log_rec, c->c_log_xavg,
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_partials2, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
-                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_nclamp_step, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump,
+                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_nclamp_step, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump, c->l_tile_thr,
                     c->r_halo, c->r_error, c->r_progress, c->r_ckpt, c->r_hist_rows, c->r_step_sums, c->r_nclamp_slots};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -284,6 +284,28 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
             CK(cudaMalloc((void **)&c->l_thr_jump, sizeof(JumpEntry) * tj.size()));
             CK(cudaMemcpy(c->l_cta_jump, cj.data(), sizeof(JumpEntry) * cj.size(), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(c->l_thr_jump, tj.data(), sizeof(JumpEntry) * tj.size(), cudaMemcpyHostToDevice));
+            if (c->tile_ok) {  // the tile kernel's per-thread table: same jump + where the strip lies in the staged tile
+                const u64 L1 = (u64)p.dims[1], R = (u64)c->m_R, w = (u64)c->m_w, rowb = L0 * 4;
+                const u64 seg_rows = rows_per_cta < L1 ? rows_per_cta : L1, seg_bytes = (seg_rows + 2) * rowb;
+                const JumpEntry rowj = jump_entry(L0);
+                std::vector<TileThread> tt(256);
+                for (u64 t = 0; t < 256; ++t) {
+                    const u64 tx = t % tpr, rt = (t / tpr) * R, x0 = tx * w, off = rt * L0 + x0;
+                    const u64 sg = rt / seg_rows, s_row = 128 + sg * seg_bytes + (1 + rt - sg * seg_rows) * rowb;
+                    TileThread &e = tt[t];
+                    e = TileThread{};
+                    e.a = tj[t].a; e.g0 = tj[t].g0; e.bg1 = tj[t].bg1;
+                    e.ck_off = LCG_BETA * off * rowj.g0;
+                    e.thr_off = (unsigned)off;
+                    e.s_c = (unsigned)(s_row + x0 * 4);
+                    e.s_left = (unsigned)(s_row + (x0 == 0 ? (L0 - 1) * 4 : x0 * 4 - 4));
+                    e.s_right = (unsigned)(s_row + (x0 + w == L0 ? 0 : (x0 + w) * 4));
+                    e.plane = (unsigned)(rt / L1);
+                    e.row = (unsigned)rt;
+                }
+                CK(cudaMalloc((void **)&c->l_tile_thr, sizeof(TileThread) * tt.size()));
+                CK(cudaMemcpy(c->l_tile_thr, tt.data(), sizeof(TileThread) * tt.size(), cudaMemcpyHostToDevice));
+            }
 
         }
     }
@@ -471,6 +493,7 @@ LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */
     A.m_tpr_log = c->m_tpr_log;
     A.cta_jump = c->l_cta_jump;
     A.thr_jump = c->l_thr_jump;
+    A.tile_thr = c->l_tile_thr;
     A.row_jump = jump_entry((u64)p.dims[0]);
     A.rebase = c->l_rebase;
     sq_fill_rebase_inline(A, nullptr, 0);

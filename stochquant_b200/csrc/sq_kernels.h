@@ -70,6 +70,17 @@ struct RebaseEntry {
     u64 vseed;
 };
 
+// lattice_tile_kernel: where a thread's first strip lies inside ANY tile (tile geometry does not depend on the CTA), built on
+// the host once per context.  64 bytes: the kernel fetches it with three 128-bit loads (+ `plane` for d = 4).
+struct alignas(64) TileThread {
+    u64 a, g0;                 // table jump over thr_off draws (JumpEntry a, g0, bg1) ...
+    u64 bg1, ck_off;           // ... and BETA thr_off row_jump.g0, the thread's share of the row-advance constant
+    unsigned thr_off, s_c;     // first site relative to the tile's first site (ty R L0 + tx w) ; byte offset of that strip ...
+    unsigned s_left, s_right;  // ... and of its two x0 neighbours inside the staged tile (from the start of dynamic smem)
+    unsigned plane, row;       // x2 planes / x1 rows between the tile's first row and the thread's first row
+    unsigned pad[2];
+};
+
 constexpr int RB_INLINE = 4;
 struct LatticeArgs {
     int ndim;            // 2..4
@@ -116,6 +127,7 @@ struct LatticeArgs {
     int m_tpr_log;               // log2(threads per row) = log2(dims[0] / m_w)
     const JumpEntry *cta_jump;   // [ctas per slice] jump over bx * rows_per_cta * L0 draws
     const JumpEntry *thr_jump;   // [256] jump over (ty * R * L0 + tx * m_w) draws
+    const TileThread *tile_thr;  // [256] tile kernel (null unless m_on == 2)
     JumpEntry row_jump;          // jump over L0 draws (one row down at fixed x0)
     u64 t_dck, t_dc1, t_dc2;     // tile kernel: per-row increments of the affine constant and of the two site constants
     // ---- multi-GPU slab ring (sq_slab.cu); slab_on == 0: everything below is unused ----------

@@ -65,6 +65,10 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+// ask L2 for a linear run of bytes ahead of the loads that will read it (no destination, no completion to wait for)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tile_mbar_wait(unsigned bar, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n"
@@ -75,52 +79,99 @@ __device__ __forceinline__ void tile_mbar_wait(unsigned bar, unsigned parity) {
 
 }  // namespace
 
+// What thread 0 works out once for the CTA (the other 255 threads used to repeat all of it: 2/3 of the ~450 instructions a
+// thread spent before its first strip, 14 per site on 64^4 -- profiles/r02_c3_tile.txt).
+struct TileHdr {
+    int skip, tl;          // an earlier launch flagged an event ; the CTA's time slice
+    unsigned bx, x2;       // tile index inside the slice ; x2 of the tile's first row
+    u64 s_cta, scg;        // seed before the tile's first draw ; BETA g_cta + GAMMA (middle term of a table jump from there)
+    u64 c1, c2, ck;        // site constants and row-advance constant of the tile's FIRST site
+    u64 g_cta;             // its gid
+    const char *cur, *tp, *tm;  // the tile's first site in the slice, the slice above, the slice below
+    char *dst;
+    const float *cur_slice;
+    unsigned o_cta, pad;   // offset of the tile's first site inside the slice (reals)
+};
+
 // L0T: row length known at compile time (0: runtime) -- the byte stride between a thread's passes becomes an immediate
 // NP: packed pairs per strip (2: four sites, 4: eight sites per thread and pass)
-// REBASE: the step has replay entries (the common, event-free instance carries none of that code)
+// (steps with replay entries are launched on the marching kernel: this one carries none of that code)
 #ifndef TILE_MINB
 #define TILE_MINB 3
 #endif
-template <int MATH, int NDIM, int POT, int L0T, int NP, bool REBASE>
-__global__ void __launch_bounds__(256, NP == 4 ? 2 : (REBASE ? 3 : TILE_MINB)) lattice_tile_kernel(const LatticeArgs A) {
+template <int MATH, int NDIM, int POT, int L0T, int NP>
+__global__ void __launch_bounds__(256, NP == 4 ? 2 : TILE_MINB) lattice_tile_kernel(const LatticeArgs A) {
     constexpr unsigned W = 2u * NP, NH = NP / 2u;  // sites per strip, float4 per strip
     extern __shared__ __align__(128) unsigned char tile_smem[];
-    __shared__ int s_skip;
-    // an earlier launch flagged an event: this one will be replayed.  ONE thread decides for the CTA -- the word may rise
-    // between two threads' reads, and a CTA that has lost the warp which issues its copies would wait for them forever.
-    if (threadIdx.x == 0) s_skip = *((volatile const u64 *)A.event_key) != NO_EVENT;
+    __shared__ TileHdr H;
     const int chain = blockIdx.z;
-    int tl;
-    unsigned bx;
-    cta_slice_position(A, tl, bx);
-    const bool edge_lo = A.slab_on && tl == 0, edge_hi = A.slab_on && tl == A.nt - 1;
-    // ---- geometry: thread (tx, ty) owns strip position x0 = W tx of rows r_start .. r_start + R - 1 ------------
     const unsigned L0 = L0T ? (unsigned)L0T : (unsigned)A.dim[0], L1 = (unsigned)A.dim[1];
     const unsigned L2 = (NDIM >= 4) ? (unsigned)A.dim[2] : 1u;
     const unsigned ROWB = L0 * 4u;  // bytes per row
-    const unsigned tx = threadIdx.x & ((1u << A.m_tpr_log) - 1u), ty = threadIdx.x >> A.m_tpr_log;
     const unsigned R = (unsigned)A.m_R;
     const unsigned rows_per_cta = (256u >> A.m_tpr_log) * R;
-    const unsigned tile_row0 = bx * rows_per_cta, r_start = tile_row0 + ty * R;
-    const long long vs = A.vslice;
-    const float *in = (const float *)A.in + (long long)chain * A.chain_stride;
-    const float *cur = in + (long long)tl * vs;
-
-    // ---- stage the tile: segments = runs of rows inside one plane, each stored as [halo_lo | rows | halo_hi] ---
-    const unsigned seg_rows = rows_per_cta < L1 ? rows_per_cta : L1, nseg = rows_per_cta / seg_rows;
-    const unsigned seg_bytes = (seg_rows + 2u) * ROWB;
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(tile_smem);
     const unsigned bar = smem0, data0 = smem0 + 128u;
-    if (threadIdx.x == 0) tile_mbar_init(bar, 1);
-    if (edge_lo | edge_hi) {  // slab ring: the neighbour's boundary slice of this step's input must have landed
-        if (threadIdx.x == 0) {
-            if (edge_lo) slab_wait(A.wait_flag[0], A.wait_tag, A.slab_error);
-            if (edge_hi) slab_wait(A.wait_flag[1], A.wait_tag, A.slab_error);
+
+    // ---- the thread's place inside a tile does not depend on the CTA: one 64-byte table entry (host-built), requested
+    // now, used behind the barrier ----
+    const char *te = (const char *)(A.tile_thr + threadIdx.x);
+    const ulonglong2 e0 = ldg128(te), e1 = ldg128(te + 16), e2 = ldg128(te + 32);
+    unsigned e_plane = 0;
+    if (NDIM >= 4) e_plane = A.tile_thr[threadIdx.x].plane;
+
+    // ---- the CTA's place: thread 0 ---------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        int tl;
+        unsigned bx;
+        cta_slice_position(A, tl, bx);
+        // an earlier launch flagged an event: this one will be replayed.  ONE thread decides for the CTA -- the word may
+        // rise between two threads' reads, and a CTA that has lost the warp which issues its copies would wait forever.
+        H.skip = *((volatile const u64 *)A.event_key) != NO_EVENT;
+        tile_mbar_init(bar, 1);
+        if (A.slab_on) {  // slab ring: the neighbour's boundary slice of this step's input must have landed
+            if (tl == 0) slab_wait(A.wait_flag[0], A.wait_tag, A.slab_error);
+            if (tl == A.nt - 1) slab_wait(A.wait_flag[1], A.wait_tag, A.slab_error);
         }
+        const long long vs = A.vslice;
+        const u64 gslice = (u64)(A.slab_t0 + tl) * (u64)vs;
+        const unsigned o_cta = bx * rows_per_cta * L0;
+        const u64 g_cta = gslice + o_cta;
+        // two precomputed jumps from gid 0: slice start, tile start (the third, to the thread's strip, is per thread)
+        const u64 s_sl = lcg_apply(A.slice_jump[tl], A.seed_in[chain], 0) & LCG_MASK;
+        H.s_cta = lcg_apply(A.cta_jump[bx], s_sl, gslice) & LCG_MASK;
+        const u64 scg = LCG_BETA * g_cta + LCG_GAMMA;
+        H.scg = scg;
+        // T(next row) = alpha^L0 T + ck ; ck itself is a running sum
+        H.ck = scg * A.row_jump.g0 + A.row_jump.bg1 - A.row_jump.a * TWO31 + TWO31;
+        // t1 = A T + c1, T' = A^2 T + c2 ; +A / +(A^2+A) per site
+        H.c1 = site_const(g_cta) - LCG_A * TWO31;
+        H.c2 = (LCG_A + 1) * site_const(g_cta) - LCG_ALPHA * TWO31;
+        H.g_cta = g_cta;
+        const float *in = (const float *)A.in + (long long)chain * A.chain_stride;
+        const float *cur = in + (long long)tl * vs;
+        const float *tm = (tl > 0) ? cur - vs : (A.wrap_time ? in + (long long)(A.nt - 1) * vs : (const float *)A.ghost_lo);
+        const float *tp = (tl < A.nt - 1) ? cur + vs : (A.wrap_time ? in : (const float *)A.ghost_hi);
+        H.cur_slice = cur;
+        H.cur = (const char *)(cur + o_cta);
+        H.tp = (const char *)(tp + o_cta);
+        H.tm = (const char *)(tm + o_cta);
+        H.dst = (char *)((float *)A.out + (long long)chain * A.chain_stride + (long long)tl * vs + o_cta);
+        H.tl = tl;
+        H.bx = bx;
+        H.x2 = (NDIM >= 4) ? (bx * rows_per_cta) / L1 : 0u;
+        H.o_cta = o_cta;
     }
     __syncthreads();
-    if (s_skip) return;
+    if (H.skip) return;
+    const int tl = H.tl;
+
+    // ---- stage the tile: segments = runs of rows inside one plane, each stored as [halo_lo | rows | halo_hi] ---
     if (threadIdx.x < 32) {
+        const unsigned seg_rows = rows_per_cta < L1 ? rows_per_cta : L1, nseg = rows_per_cta / seg_rows;
+        const unsigned seg_bytes = (seg_rows + 2u) * ROWB;
+        const unsigned tile_row0 = H.bx * rows_per_cta;
+        const float *cur = H.cur_slice;
         if (threadIdx.x == 0) tile_expect_tx(bar, nseg * seg_bytes);
         __syncwarp();
         for (unsigned c = threadIdx.x; c < 3u * nseg; c += 32u) {
@@ -133,62 +184,52 @@ __global__ void __launch_bounds__(256, NP == 4 ? 2 : (REBASE ? 3 : TILE_MINB)) l
             else { src_row = (x1a + seg_rows == L1) ? prow0 : row0 + seg_rows; dst_off = (seg_rows + 1u) * ROWB; bytes = ROWB; }
             bulk_g2s(data0 + sg * seg_bytes + dst_off, cur + (size_t)src_row * L0, bytes, bar);
         }
+#ifndef TILE_NO_PREFETCH
+        // the four streams without reuse are read straight from global memory, a pass at a time: ask L2 for the tile's
+        // share of them now (the slice above / below: one run; the planes above / below: one run per segment)
+        if (threadIdx.x == 30) bulk_prefetch_l2(H.tp, rows_per_cta * ROWB);
+        if (threadIdx.x == 31) bulk_prefetch_l2(H.tm, rows_per_cta * ROWB);
+        if (NDIM >= 4) {
+            const long long planeR = (long long)L0 * L1, wrapR = (long long)(L2 - 1) * planeR;
+            for (unsigned c = threadIdx.x; c < 2u * nseg; c += 32u) {
+                const unsigned sg = c >> 1, row0 = tile_row0 + sg * seg_rows, x2s = row0 / L1;
+                const float *base = cur + (size_t)row0 * L0;
+                const float *q = (c & 1) ? base + ((x2s == 0) ? wrapR : -planeR) : base + ((x2s + 1 == L2) ? -wrapR : planeR);
+                bulk_prefetch_l2(q, seg_rows * ROWB);
+            }
+        }
+#endif
     }
 
-    unsigned x2 = 0;
-    if (NDIM >= 4) x2 = r_start / L1;
-    const unsigned x0 = tx * W;
-    const float *tm = (tl > 0) ? cur - vs : (A.wrap_time ? in + (long long)(A.nt - 1) * vs : (const float *)A.ghost_lo);
-    const float *tp = (tl < A.nt - 1) ? cur + vs : (A.wrap_time ? in : (const float *)A.ghost_hi);
-    float *dst = (float *)A.out + (long long)chain * A.chain_stride + (long long)tl * vs;
-    const bool push_lo = edge_lo && A.push_tag, push_hi = edge_hi && A.push_tag;
-    const unsigned plane = L0 * L1;
-    const unsigned o0 = r_start * L0 + x0;  // offset of the thread's first strip inside the slice (reals)
-    unsigned o = o0;                        // (REBASE) offset of the strip in hand
+    // ---- the thread's first strip: stream bases, staged-tile addresses, chain state ---------------------------
+    const unsigned thr_off = (unsigned)e2.x;   // first site relative to the tile's first site (reals)
+    const u64 bo = (u64)thr_off * 4u;
     // per-thread stream bases (bytes); pass k adds k * ROWB
-    const char *p_tp = (const char *)(tp + o0), *p_tm = (const char *)(tm + o0);
+    const char *p_tp = H.tp + bo, *p_tm = H.tm + bo;
     const char *p_u2 = nullptr, *p_d2 = nullptr;
     if (NDIM >= 4) {
-        p_u2 = (const char *)(cur + o0) + (long long)((x2 + 1 == L2) ? -(long long)(L2 - 1) * plane : (long long)plane) * 4;
-        p_d2 = (const char *)(cur + o0) + (long long)((x2 == 0) ? (long long)(L2 - 1) * plane : -(long long)plane) * 4;
+        const unsigned x2 = H.x2 + e_plane;
+        const long long planeB = (long long)L0 * L1 * 4, wrapB = (long long)(L2 - 1) * planeB;
+        p_u2 = H.cur + bo + ((x2 + 1 == L2) ? -wrapB : planeB);
+        p_d2 = H.cur + bo + ((x2 == 0) ? wrapB : -planeB);
     }
-    char *p_dst = (char *)(dst + o0);
+    char *p_dst = H.dst + bo;
     // shared-memory addresses of the thread's first strip and its x0 neighbours
-    const unsigned rt = ty * R;  // row inside the tile
-    const unsigned sg_t = rt / seg_rows;
-    const unsigned s_row = data0 + sg_t * seg_bytes + (1u + rt - sg_t * seg_rows) * ROWB;
-    unsigned s_c = s_row + x0 * 4u;
-    unsigned s_left = s_row + ((x0 == 0) ? (L0 - 1u) * 4u : x0 * 4u - 4u);
-    unsigned s_right = s_row + ((x0 + W == L0) ? 0u : (x0 + W) * 4u);
+    unsigned s_c = smem0 + (unsigned)(e2.x >> 32), s_left = smem0 + (unsigned)e2.y, s_right = smem0 + (unsigned)(e2.y >> 32);
+    const bool push_lo = A.slab_on && tl == 0 && A.push_tag, push_hi = A.slab_on && tl == A.nt - 1 && A.push_tag;
 
     // ---- chain state: T = seed before the thread's first draw + 2^31, per-row affine advance ------------------
-    const u64 gslice = (u64)(A.slab_t0 + tl) * (u64)vs;
-    const u64 S = A.seed_in[chain];
-    unsigned cnt_prev = 0, nxt32 = 0x7FFFFFFFu;
-    u64 S_eff = S;
-    if (REBASE) {
-        const Rebased rb = rebase_eval(A.rebase, A.n_rebase, chain, S, gslice + o0, gslice, (unsigned)vs, W);
-        S_eff = rb.S_eff;
-        cnt_prev = rb.cnt;
-        nxt32 = rb.slow ? o0 : rb.nxt32;  // an entry inside the first strip: take the rare path at k == 0
-    }
-    // three precomputed jumps from gid 0: slice start, CTA's first row, this thread's first strip
     unsigned Tl, Th;
     {
-        const u64 g_cta = gslice + (u64)bx * rows_per_cta * L0;
-        const u64 s_sl = lcg_apply(A.slice_jump[tl], S_eff, 0) & LCG_MASK;
-        const u64 s_cta = lcg_apply(A.cta_jump[bx], s_sl, gslice) & LCG_MASK;
-        const u64 s = lcg_apply(A.thr_jump[threadIdx.x], s_cta, g_cta) & LCG_MASK;
+        const u64 s = (e0.x * H.s_cta + H.scg * e0.y + e1.x) & LCG_MASK;  // the table jump over thr_off draws
         const u64 T = s + TWO31;
         Tl = (unsigned)T;
         Th = (unsigned)(T >> 32);
     }
     const unsigned aDl = (unsigned)A.row_jump.a, aDh = (unsigned)(A.row_jump.a >> 32);
-    // T(next row) = alpha^L0 T + ck ; ck itself is a running sum
-    u64 ck = (LCG_BETA * (gslice + o0) + LCG_GAMMA) * A.row_jump.g0 + A.row_jump.bg1 - A.row_jump.a * TWO31 + TWO31;
-    // site constants of the strip's first site: t1 = A T + c1, T' = A^2 T + c2 ; +A / +(A^2+A) per site
-    u64 c1 = site_const(gslice + o0) - LCG_A * TWO31;
-    u64 c2 = (LCG_A + 1) * site_const(gslice + o0) - LCG_ALPHA * TWO31;
+    u64 ck = H.ck + e1.y;               // + BETA thr_off row_jump.g0
+    u64 c1 = H.c1 + LCG_A * thr_off;    // site constants of the strip's first site
+    u64 c2 = H.c2 + LCG_BETA * thr_off;
     // (the per-row increments A.t_dck, A.t_dc1 = (L0 - (W-1)) A, A.t_dc2 = (L0 - (W-1))(A^2 + A) are kernel parameters:
     // constant-bank operands of the adds, not registers)
 
@@ -307,7 +348,7 @@ __global__ void __launch_bounds__(256, NP == 4 ? 2 : (REBASE ? 3 : TILE_MINB)) l
             bool replayed = false;  // an event in this strip: the launch is redone, its clamp hits are not counted
             if (um < 32768u) {
                 const u64 z0 = ((((u64)T0h << 32) | T0l) - TWO31) & LCG_MASK;
-                replayed = strip_events_cold(A.event_key, A.step_index, chain, z0, (u64)(A.slab_t0 + tl) * (u64)A.vslice + o0 + k * L0, (int)W);
+                replayed = strip_events_cold(A.event_key, A.step_index, chain, z0, H.g_cta + thr_off + k * L0, (int)W);
             }
 #pragma unroll
             for (unsigned h = 0; h < NH; ++h) {
@@ -323,7 +364,7 @@ __global__ void __launch_bounds__(256, NP == 4 ? 2 : (REBASE ? 3 : TILE_MINB)) l
 #pragma unroll
         for (unsigned h = 0; h < NH; ++h) *reinterpret_cast<ulonglong2 *>(p_dst + kb + 16u * h) = make_ulonglong2(V[2 * h], V[2 * h + 1]);
         if (__builtin_expect(push_lo | push_hi, 0)) {  // CTA-uniform: boundary slices of a slab ring only
-            const size_t oo = (size_t)(o0 + k * L0) * 4u;
+            const size_t oo = (size_t)(H.o_cta + thr_off + k * L0) * 4u;
 #pragma unroll
             for (unsigned h = 0; h < NH; ++h) {
                 if (push_lo) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[0] + oo + 16u * h) = make_ulonglong2(V[2 * h], V[2 * h + 1]);
@@ -332,80 +373,13 @@ __global__ void __launch_bounds__(256, NP == 4 ? 2 : (REBASE ? 3 : TILE_MINB)) l
         }
     };
 
-    // ---- a whole strip on the rare path (a replay entry's first site or its overridden site lies inside it) ----
-    auto slow_strip = [&](const unsigned k) {
-        const unsigned x1 = ((NDIM >= 4) ? (r_start - x2 * L1) : r_start) + k;
-        const u64 gsl = (u64)(A.slab_t0 + tl) * (u64)A.vslice;
-        const u64 g0 = gsl + o;
-        const Rebased rb = rebase_eval(A.rebase, A.n_rebase, chain, A.seed_in[chain], g0, gsl, (unsigned)A.vslice, W);
-        nxt32 = rb.nxt32;
-        if (rb.cnt != cnt_prev) {  // new base: the thread's first strip under the new start seed, k rows down
-            cnt_prev = rb.cnt;
-            const u64 gc = gsl + (u64)bx * rows_per_cta * L0;
-            const u64 s_sl = lcg_apply(A.slice_jump[tl], rb.S_eff, 0) & LCG_MASK;
-            const u64 s_cta = lcg_apply(A.cta_jump[bx], s_sl, gsl) & LCG_MASK;
-            u64 t = (lcg_apply(A.thr_jump[threadIdx.x], s_cta, gc) & LCG_MASK) + TWO31;
-            u64 cj = (LCG_BETA * (g0 - (u64)k * L0) + LCG_GAMMA) * A.row_jump.g0 + A.row_jump.bg1 - A.row_jump.a * TWO31 + TWO31;
-            for (unsigned j = 0; j < k; ++j) {
-                t = A.row_jump.a * t + cj;
-                cj += A.t_dck;
-            }
-            Tl = (unsigned)t;
-            Th = (unsigned)(t >> 32);
-        }
-        if (!rb.slow) return false;
-        // the whole strip out of line, four sites at a time; the row recurrence is void behind an entry (re-evaluated at
-        // the next strip)
-        const unsigned row_wrap = (L1 - 1) * L0;
-        u64 sq = ((((u64)Th << 32) | Tl) - TWO31) & LCG_MASK;
-#pragma unroll 1
-        for (unsigned h = 0; h < NH; ++h) {
-            const unsigned oh = o + 4u * h, xh = x0 + 4u * h;
-            SlowIn I;
-            I.cur = cur; I.tm = tm; I.tp = tp; I.dst = dst;
-            I.push0 = push_lo ? (float *)A.push_ghost[0] : nullptr;
-            I.push1 = push_hi ? (float *)A.push_ghost[1] : nullptr;
-            I.o = oh;
-            I.o_up1 = oh + ((x1 + 1 == L1) ? 0u - row_wrap : L0);
-            I.o_dn1 = oh + ((x1 == 0) ? row_wrap : 0u - L0);
-            I.o_up2 = (NDIM >= 4) ? oh + ((x2 + 1 == L2) ? 0u - (L2 - 1) * plane : plane) : 0u;
-            I.o_dn2 = (NDIM >= 4) ? oh + ((x2 == 0) ? (L2 - 1) * plane : 0u - plane) : 0u;
-            I.o_left = oh + ((xh == 0) ? L0 - 1u : 0u - 1u);
-            I.o_right = oh + ((xh + 4 == L0) ? 4u - L0 : 4u);
-            I.s = sq;
-            I.g0 = g0 + 4u * h;
-            I.chain = chain; I.step_index = A.step_index; I.n_rebase = A.n_rebase;
-            I.rebase = A.rebase; I.event_key = A.event_key;
-            I.c_lap = c_lap; I.c_dt = c_dt; I.m2 = m2; I.lam = lam; I.k2 = A.k2_f; I.nscale = A.nscale;
-            const SlowOut so = strip_slow<MATH, NDIM, POT>(I);
-            ACC1 = add2(ACC1, pk(so.a1, 0.f));
-            ACC2 = add2(ACC2, pk(so.a2, 0.f));
-            nclamp += so.nclamp;
-            sq = so.s_after;
-        }
-        nxt32 = o + L0;  // re-evaluate at the next strip (new base)
-        ck += A.t_dck;
-        c1 += (u64)L0 * LCG_A;
-        c2 += (u64)L0 * LCG_BETA;
-        return true;
-    };
-
     tile_mbar_wait(bar, 0);  // the tile has landed (other CTAs of the SM computed meanwhile)
     // ---- the thread's R strips: U passes per trip (pass offsets are immediates), then the stream bases move on --------
-    // (R is a multiple of 4 -- tile_shape_ok -- so the event-free instance needs no tail test)
-    constexpr unsigned U = REBASE ? 1u : (NP == 4 ? 2u : 4u);
+    // (R is a multiple of 4 -- tile_shape_ok -- so there is no tail test)
+    constexpr unsigned U = NP == 4 ? 2u : 4u;
     for (unsigned k0 = 0; k0 < R; k0 += U) {
 #pragma unroll
-        for (unsigned u = 0; u < U; ++u) {
-            // replay entries: a thread visits its strips in increasing gid, so it only watches the distance to the NEXT
-            // entry (32-bit, relative to the slice); reaching one re-evaluates the base with the full 64-bit logic
-            bool done = false;
-            if (REBASE) {
-                o = o0 + (k0 + u) * L0;
-                if (__builtin_expect((int)(nxt32 - o) <= (int)W, 0)) done = slow_strip(k0 + u);
-            }
-            if (!done) pass(u * ROWB, k0 + u);
-        }
+        for (unsigned u = 0; u < U; ++u) pass(u * ROWB, k0 + u);
         p_tp += U * ROWB;
         p_tm += U * ROWB;
         if (NDIM >= 4) {
@@ -439,30 +413,13 @@ __global__ void __launch_bounds__(256, NP == 4 ? 2 : (REBASE ? 3 : TILE_MINB)) l
     }
 
     // ---- the omega work-item's draw (gid = V) and the step's final seed -------------------------------------
-    if (bx == 0 && tl == 0 && threadIdx.x == 0) {
+    if (threadIdx.x == 0 && H.bx == 0 && tl == 0) {
         const u64 Vg = (u64)A.V;
-        u64 sv, t1, t2;
-        bool overridden = false;
-        u64 next = 0;
-        if (REBASE) {
-            u64 bg, bs;
-            rebase_lookup(A, chain, S, Vg, bg, bs);
-            sv = lcg_seed_at(bs, bg, Vg - bg, A.jump);
-            for (int j = 0; j < A.n_rebase; ++j)
-                if (A.rebase[j].chain == chain && A.rebase[j].ov_gid == Vg) {
-                    overridden = true;
-                    next = A.rebase[j].seed;  // entry with gid_start == V+1
-                }
-        } else {
-            sv = lcg_apply(A.vol_jump, S, 0) & LCG_MASK;
-        }
+        u64 t1, t2;
+        const u64 sv = lcg_apply(A.vol_jump, A.seed_in[chain], 0) & LCG_MASK;
         lcg_draw(sv, Vg, t1, t2);
-        if (!overridden) {
-            if (lcg_event(sv & LCG_MASK, t1, t2))
-                atomicMin((unsigned long long *)A.event_key, event_key(A.step_index, chain, Vg));
-            next = lcg_next_seed(t2);
-        }
-        A.seed_out[chain] = next;
+        if (lcg_event(sv & LCG_MASK, t1, t2)) atomicMin((unsigned long long *)A.event_key, event_key(A.step_index, chain, Vg));
+        A.seed_out[chain] = lcg_next_seed(t2);
     }
 
     // ---- per-CTA observable partial ---------------------------------------------------------------------------
@@ -478,7 +435,7 @@ __global__ void __launch_bounds__(256, NP == 4 ? 2 : (REBASE ? 3 : TILE_MINB)) l
         if (threadIdx.x == 0) {
             double s1 = 0, s2 = 0;
             for (int q = 0; q < 8; ++q) { s1 += red[0][q]; s2 += red[1][q]; }
-            double *p = A.partials + (((long long)chain * A.nt + tl) * gridDim.x + bx) * 2;
+            double *p = A.partials + (((long long)chain * A.nt + tl) * gridDim.x + H.bx) * 2;
             p[0] = s1;
             p[1] = s2;
         }
@@ -507,10 +464,10 @@ bool tile_shape_ok(int L0, int L1, int tpr_log, int R) {
 template <int MATH, int NDIM, int POT, int L0T>
 static cudaError_t tile_go(const LatticeArgs &A, dim3 grid, size_t smem, cudaStream_t st) {
     if (smem > 48 * 1024) {  // (idempotent; the attribute is per function)
-        cudaError_t e = cudaFuncSetAttribute(lattice_tile_kernel<MATH, NDIM, POT, L0T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(lattice_tile_kernel<MATH, NDIM, POT, L0T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
         if (e != cudaSuccess) return e;
     }
-    lattice_tile_kernel<MATH, NDIM, POT, L0T, 2, false><<<grid, 256, smem, st>>>(A);
+    lattice_tile_kernel<MATH, NDIM, POT, L0T, 2><<<grid, 256, smem, st>>>(A);
     return cudaGetLastError();
 }
 template <int MATH, int NDIM, int POT>
