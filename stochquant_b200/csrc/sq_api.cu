@@ -105,7 +105,7 @@ extern "C" void sq_free(sq_ctx *c) {
                     c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps, c->c_ctl, c->c_log_rec, c->c_log_xavg,
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_partials2, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
-                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_nclamp_step, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump, c->l_tile_thr,
+                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_nclamp_step, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump, c->l_tile_thr, c->l_tile_ctr,
                     c->r_halo, c->r_error, c->r_progress, c->r_ckpt, c->r_hist_rows, c->r_step_sums, c->r_nclamp_slots};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -303,6 +303,8 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
                     e.plane = (unsigned)(rt / L1);
                     e.row = (unsigned)rt;
                 }
+                CK(cudaMalloc((void **)&c->l_tile_ctr, 2 * sizeof(unsigned)));
+                CK(cudaMemset(c->l_tile_ctr, 0, 2 * sizeof(unsigned)));
                 CK(cudaMalloc((void **)&c->l_tile_thr, sizeof(TileThread) * tt.size()));
                 CK(cudaMemcpy(c->l_tile_thr, tt.data(), sizeof(TileThread) * tt.size(), cudaMemcpyHostToDevice));
             }
@@ -494,6 +496,7 @@ LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */
     A.cta_jump = c->l_cta_jump;
     A.thr_jump = c->l_thr_jump;
     A.tile_thr = c->l_tile_thr;
+    A.tile_ctr = c->l_tile_ctr;
     A.row_jump = jump_entry((u64)p.dims[0]);
     A.rebase = c->l_rebase;
     sq_fill_rebase_inline(A, nullptr, 0);

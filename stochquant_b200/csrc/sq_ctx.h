@@ -81,6 +81,7 @@ struct sq_ctx {
     bool tile_ok = false;   // ... and its tiles can be staged in shared memory: lattice_tile_kernel (sq_tile.cu)
     int m_R = 0, m_tpr_log = 0, m_w = 4;
     JumpEntry *l_cta_jump = nullptr, *l_thr_jump = nullptr;
+    unsigned *l_tile_ctr = nullptr;    // [2] persistent tile kernel's claim counters
     sq::TileThread *l_tile_thr = nullptr;  // [256] tile kernel: a thread's place inside any tile
     // resident 2-D path (sq_resident.cu)
     bool res_ok = false;

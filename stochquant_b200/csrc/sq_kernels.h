@@ -128,6 +128,7 @@ struct LatticeArgs {
     const JumpEntry *cta_jump;   // [ctas per slice] jump over bx * rows_per_cta * L0 draws
     const JumpEntry *thr_jump;   // [256] jump over (ty * R * L0 + tx * m_w) draws
     const TileThread *tile_thr;  // [256] tile kernel (null unless m_on == 2)
+    unsigned *tile_ctr;          // [2] persistent tile kernel: next tile to claim, CTAs that have finished (both 0 between launches)
     JumpEntry row_jump;          // jump over L0 draws (one row down at fixed x0)
     u64 t_dck, t_dc1, t_dc2;     // tile kernel: per-row increments of the affine constant and of the two site constants
     // ---- multi-GPU slab ring (sq_slab.cu); slab_on == 0: everything below is unused ----------

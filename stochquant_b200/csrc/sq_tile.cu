@@ -21,6 +21,9 @@
 //     halves, and the noise phase that covers the global loads' latency doubles.
 // CTA -> tile mapping, jump tables, per-CTA observable partials, clamp slots, replay entries (REBASE), L2
 // chunking and the slab ring's halo protocol are those of the marching kernel, so the host side is shared.
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "sq_strip_slow.cuh"
 
 namespace sq {
@@ -443,14 +446,445 @@ __global__ void __launch_bounds__(256, NP == 4 ? 2 : TILE_MINB) lattice_tile_ker
     if (nclamp) atomicAdd(A.nclamped, (unsigned long long)nclamp);
 }
 
-// shared memory a CTA needs: one mbarrier line + [halo | rows | halo] per run of rows inside a plane
-size_t tile_smem_bytes(int L0, int L1, int tpr_log, int R) {
+// =====================================================================================================================
+// Persistent form: one CTA per slot of the GPU (3 per SM), each working through tiles in TWO shared-memory stages.  What a
+// CTA of the one-tile kernel spends before its first strip -- header, copy issue, a DRAM round trip: about a fifth of its
+// life on 64^4, with a third of the SM's warps parked meanwhile -- is done for the next tile while this one is computed:
+//   * full[s] / empty[s] mbarriers per stage: the producer arms full[s] with the byte count and issues the bulk copies; the
+//     256 computing threads wait on it, compute, and each warp's lane 0 arrives on empty[s] (count 8);
+//   * the producer is a ninth warp: it waits for empty[s] (everybody has left the tile before last), writes that tile's
+//     observable partial and slab-ring flag, CLAIMS the next tile from a counter, computes its header, issues its copies and
+//     asks L2 for its share of the four streams that are read straight from global memory -- up to two tiles ahead of use;
+//   * no CTA-wide barrier after the first.
+// Tiles are claimed in order, as stages come free -- what the hardware does with CTAs -- so the tiles in flight stay one
+// contiguous window of the one-tile kernel's CTA order (cta_slice_position: L2 chunks swept through the time slices, a slab
+// ring's boundary slices first; chains outermost).  Partials, clamp slots and jump tables are unchanged.
+// Measured dead ends, 256^3 x 32 slices, one-tile kernel = 384 G site-updates/s:
+//   - a FIXED stride (tile = blockIdx.x + i gridDim.x): 209.  The CTAs drift apart over their ~150 tiles, the L2 chunk order
+//     then means nothing and every site comes from HBM three times (6.6 GB read per step instead of 2.6, ncu);
+//   - the producer role rotating over the eight computing warps instead of a ninth warp: 219 (same drift, and whoever
+//     produces falls behind by the header's latency -- the next producer has to wait for exactly that warp).
+struct PTileShared {
+    TileHdr H[2];
+    double red[2][2][8];
+    int chain[2];
+    int end[2];   // the stage holds no tile: the grid has run out of them
+    int skip;
+};
+
+__device__ __forceinline__ void tile_mbar_arrive(unsigned bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+
+template <int MATH, int NDIM, int POT, int L0T>
+__global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs A, const unsigned ntiles, const unsigned cps, const unsigned stage_stride, const unsigned pf) {
+    constexpr unsigned NP = 2, W = 4;
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ PTileShared S;
+    const unsigned L0 = L0T ? (unsigned)L0T : (unsigned)A.dim[0], L1 = (unsigned)A.dim[1];
+    const unsigned L2 = (NDIM >= 4) ? (unsigned)A.dim[2] : 1u;
+    const unsigned ROWB = L0 * 4u;
+    const unsigned R = (unsigned)A.m_R;
+    const unsigned rows_per_cta = (256u >> A.m_tpr_log) * R;
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(tile_smem);
+    // mbarriers: full[0], full[1], empty[0], empty[1] at smem0 + 0 / 8 / 16 / 24 ; stage s data at smem0 + 128 + s * stage_stride
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+
+    if (threadIdx.x == 0) {
+        // an earlier launch flagged an event: this one will be replayed
+        S.skip = *((volatile const u64 *)A.event_key) != NO_EVENT;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem0) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem0 + 8u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem0 + 16u) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem0 + 24u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (S.skip) return;
+
+    if (warp == 8) {  // ================= the producer warp: up to two tiles ahead of the eight that compute =================
+        // ---- tile `lin` into stage st: header (lane 0), copies and L2 prefetches (all lanes) ----
+        auto produce = [&](unsigned lin, const unsigned st) {
+            TileHdr &H = S.H[st];
+            if (lane == 0) {
+                S.end[st] = 0;
+                const unsigned per_chain = cps * (unsigned)A.nt;
+                const unsigned chain = lin / per_chain;
+                lin -= chain * per_chain;
+                int tl = 0;
+                unsigned bx = 0;
+                {   // cta_slice_position for a linear tile index
+                    unsigned t_first = 0, nt_sweep = (unsigned)A.nt;
+                    bool done = false;
+                    if (A.slab_on && A.nt > 1) {
+                        if (lin < 2 * cps) {
+                            tl = (lin < cps) ? 0 : A.nt - 1;
+                            bx = (lin < cps) ? lin : lin - cps;
+                            done = true;
+                        } else {
+                            lin -= 2 * cps;
+                            t_first = 1;
+                            nt_sweep = (unsigned)A.nt - 2;
+                        }
+                    }
+                    if (!done) {
+                        const unsigned cpc = (unsigned)A.ctas_per_chunk;
+                        const unsigned per_chunk = cpc * nt_sweep;
+                        const unsigned chunk = lin / per_chunk;
+                        const unsigned rem = lin - chunk * per_chunk;
+                        const unsigned width = (chunk * cpc + cpc <= cps) ? cpc : cps - chunk * cpc;  // the last chunk may be narrower
+                        const unsigned ty = rem / width;
+                        tl = (int)(t_first + ty);
+                        bx = chunk * cpc + (rem - ty * width);
+                    }
+                }
+                if (A.slab_on) {  // slab ring: the neighbour's boundary slice of this step's input must have landed
+                    if (tl == 0) slab_wait(A.wait_flag[0], A.wait_tag, A.slab_error);
+                    if (tl == A.nt - 1) slab_wait(A.wait_flag[1], A.wait_tag, A.slab_error);
+                }
+                const long long vs = A.vslice;
+                const u64 gslice = (u64)(A.slab_t0 + tl) * (u64)vs;
+                const unsigned o_cta = bx * rows_per_cta * L0;
+                const u64 g_cta = gslice + o_cta;
+                const u64 s_sl = lcg_apply(A.slice_jump[tl], A.seed_in[chain], 0) & LCG_MASK;
+                H.s_cta = lcg_apply(A.cta_jump[bx], s_sl, gslice) & LCG_MASK;
+                const u64 scg = LCG_BETA * g_cta + LCG_GAMMA;
+                H.scg = scg;
+                H.ck = scg * A.row_jump.g0 + A.row_jump.bg1 - A.row_jump.a * TWO31 + TWO31;
+                H.c1 = site_const(g_cta) - LCG_A * TWO31;
+                H.c2 = (LCG_A + 1) * site_const(g_cta) - LCG_ALPHA * TWO31;
+                H.g_cta = g_cta;
+                const float *in = (const float *)A.in + (long long)chain * A.chain_stride;
+                const float *cur = in + (long long)tl * vs;
+                const float *tm = (tl > 0) ? cur - vs : (A.wrap_time ? in + (long long)(A.nt - 1) * vs : (const float *)A.ghost_lo);
+                const float *tp = (tl < A.nt - 1) ? cur + vs : (A.wrap_time ? in : (const float *)A.ghost_hi);
+                H.cur_slice = cur;
+                H.cur = (const char *)(cur + o_cta);
+                H.tp = (const char *)(tp + o_cta);
+                H.tm = (const char *)(tm + o_cta);
+                H.dst = (char *)((float *)A.out + (long long)chain * A.chain_stride + (long long)tl * vs + o_cta);
+                H.tl = tl;
+                H.bx = bx;
+                H.x2 = (NDIM >= 4) ? (bx * rows_per_cta) / L1 : 0u;
+                H.o_cta = o_cta;
+                S.chain[st] = (int)chain;
+            }
+            __syncwarp();
+            const unsigned seg_rows = rows_per_cta < L1 ? rows_per_cta : L1, nseg = rows_per_cta / seg_rows;
+            const unsigned seg_bytes = (seg_rows + 2u) * ROWB;
+            const unsigned tile_row0 = H.bx * rows_per_cta;
+            const float *cur = H.cur_slice;
+            const unsigned bar = smem0 + 8u * st, data0 = smem0 + 128u + st * stage_stride;
+            if (lane == 0) tile_expect_tx(bar, nseg * seg_bytes);  // (release: the header is visible to whoever sees the phase end)
+            __syncwarp();
+            for (unsigned c = lane; c < 3u * nseg; c += 32u) {
+                const unsigned sg = c / 3u, part = c - 3u * sg;            // 0 rows, 1 halo below, 2 halo above
+                const unsigned row0 = tile_row0 + sg * seg_rows;            // first row of the run (row index inside the slice)
+                const unsigned x1a = row0 % L1, prow0 = row0 - x1a;         // its x1, first row of its plane
+                unsigned src_row, dst_off, bytes;
+                if (part == 0) { src_row = row0; dst_off = ROWB; bytes = seg_rows * ROWB; }
+                else if (part == 1) { src_row = (x1a == 0) ? prow0 + L1 - 1u : row0 - 1u; dst_off = 0; bytes = ROWB; }
+                else { src_row = (x1a + seg_rows == L1) ? prow0 : row0 + seg_rows; dst_off = (seg_rows + 1u) * ROWB; bytes = ROWB; }
+                bulk_g2s(data0 + sg * seg_bytes + dst_off, cur + (size_t)src_row * L0, bytes, bar);
+            }
+            if (lane == 30 && (pf & 1u)) bulk_prefetch_l2(H.tp, rows_per_cta * ROWB);
+            if (lane == 31 && (pf & 2u)) bulk_prefetch_l2(H.tm, rows_per_cta * ROWB);
+            if (NDIM >= 4 && (pf & 4u)) {
+                const long long planeR = (long long)L0 * L1, wrapR = (long long)(L2 - 1) * planeR;
+                for (unsigned c = lane; c < 2u * nseg; c += 32u) {
+                    const unsigned sg = c >> 1, row0 = tile_row0 + sg * seg_rows, x2s = row0 / L1;
+                    const float *base = cur + (size_t)row0 * L0;
+                    const float *q = (c & 1) ? base + ((x2s == 0) ? wrapR : -planeR) : base + ((x2s + 1 == L2) ? -wrapR : planeR);
+                    bulk_prefetch_l2(q, seg_rows * ROWB);
+                }
+            }
+        };
+        // ---- everybody has left the tile in stage st: its observable partial, and a slab ring's flag (lane 0) ----
+        auto retire = [&](const unsigned st) {
+            if (lane != 0) return;
+            const TileHdr &H = S.H[st];
+            const int tl = H.tl, chain = S.chain[st];
+            if (A.partials) {
+                double s1 = 0, s2 = 0;
+                for (int q = 0; q < 8; ++q) { s1 += S.red[st][0][q]; s2 += S.red[st][1][q]; }
+                double *p = A.partials + (((long long)chain * A.nt + tl) * cps + H.bx) * 2;
+                p[0] = s1;
+                p[1] = s2;
+            }
+            const bool push_lo = A.slab_on && tl == 0 && A.push_tag, push_hi = A.slab_on && tl == A.nt - 1 && A.push_tag;
+            if (push_lo || push_hi) {  // last tile of the slice: everything is out, raise the neighbour's flag
+                __threadfence_system();
+                if (push_lo && atomicAdd(A.push_count + 0, 1u) == cps - 1) {
+                    A.push_count[0] = 0;
+                    __threadfence_system();
+                    st_release_sys_u32(A.push_flag[0], A.push_tag);
+                }
+                if (push_hi && atomicAdd(A.push_count + 1, 1u) == cps - 1) {
+                    A.push_count[1] = 0;
+                    __threadfence_system();
+                    st_release_sys_u32(A.push_flag[1], A.push_tag);
+                }
+            }
+        };
+        unsigned n = 0;
+#pragma unroll 1
+        for (;;) {
+            const unsigned st = n & 1u;
+            if (n >= 2) {
+                tile_mbar_wait(smem0 + 16u + 8u * st, ((n - 2) >> 1) & 1u);  // everybody has left tile n-2
+                retire(st);
+                __syncwarp();
+            }
+            unsigned lin = 0;
+            if (lane == 0) lin = atomicAdd(A.tile_ctr, 1u);
+            lin = __shfl_sync(0xFFFFFFFFu, lin, 0);
+            if (lin >= ntiles) {
+                if (lane == 0) {
+                    S.end[st] = 1;
+                    tile_mbar_arrive(smem0 + 8u * st);  // (count 1: the phase ends, the eight warps see `end`)
+                }
+                break;
+            }
+            produce(lin, st);
+            ++n;
+        }
+        if (n >= 1) {  // the last tile's partial and flag
+            tile_mbar_wait(smem0 + 16u + 8u * ((n - 1) & 1u), ((n - 1) >> 1) & 1u);
+            retire((n - 1) & 1u);
+        }
+        // the last CTA out rearms the counters for the next launch on the stream
+        if (lane == 0 && atomicAdd(A.tile_ctr + 1, 1u) == gridDim.x - 1) {
+            A.tile_ctr[0] = 0;
+            A.tile_ctr[1] = 0;
+        }
+        return;
+    }
+
+    // ================================ the eight computing warps ===================================================
+    unsigned nclamp = 0;
+    const unsigned aDl = (unsigned)A.row_jump.a, aDh = (unsigned)(A.row_jump.a >> 32);
+    const float c_lap = (float)A.c_lap, c_dt = (float)A.c_dt;
+    const pair_t K_m2d = pk(-(float)(2 * NDIM), -(float)(2 * NDIM)), K_clap = pk(c_lap, c_lap);
+    const pair_t K_m2cdt = pk(-2.0f * c_dt, -2.0f * c_dt), K_mcdt = pk(-c_dt, -c_dt), K_m1 = pk(-1.0f, -1.0f);
+    const pair_t K_2m32 = pk(2.3283064365386963e-10f, 2.3283064365386963e-10f), K_k2 = pk(A.k2_f, A.k2_f);
+    const float kth = (float)(2.0 * 3.1415 / 4294967296.0);  // theta - pi = 2*3.1415 v2 - pi, v2 = (float)u2 * 2^-32
+    const pair_t K_th = pk(kth, kth), K_mpi = pk(-3.14159265358979f, -3.14159265358979f);
+    (void)K_m2cdt; (void)K_mcdt; (void)K_2m32; (void)K_k2; (void)K_th; (void)K_mpi;
+    const char *te = (const char *)(A.tile_thr + threadIdx.x);
+
+#pragma unroll 1
+    for (unsigned i = 0;; ++i) {
+        const unsigned st = i & 1u;
+        // the thread's place inside a tile: one 64-byte table entry (L1-resident after the first tile)
+        const ulonglong2 e0 = ldg128(te), e1 = ldg128(te + 16), e2 = ldg128(te + 32);
+        unsigned e_plane = 0;
+        if (NDIM >= 4) e_plane = A.tile_thr[threadIdx.x].plane;
+        tile_mbar_wait(smem0 + 8u * st, (i >> 1) & 1u);  // header written, tile landed
+        if (S.end[st]) break;
+        const TileHdr &H = S.H[st];
+        const int chain = S.chain[st];
+        const int tl = H.tl;
+
+        // ---- the thread's first strip: stream bases, staged-tile addresses, chain state ---------------------------
+        const unsigned thr_off = (unsigned)e2.x;
+        const u64 bo = (u64)thr_off * 4u;
+        const char *p_tp = H.tp + bo, *p_tm = H.tm + bo;
+        const char *p_u2 = nullptr, *p_d2 = nullptr;
+        if (NDIM >= 4) {
+            const unsigned x2 = H.x2 + e_plane;
+            const long long planeB = (long long)L0 * L1 * 4, wrapB = (long long)(L2 - 1) * planeB;
+            p_u2 = H.cur + bo + ((x2 + 1 == L2) ? -wrapB : planeB);
+            p_d2 = H.cur + bo + ((x2 == 0) ? wrapB : -planeB);
+        }
+        char *p_dst = H.dst + bo;
+        const unsigned sbase = smem0 + st * stage_stride;
+        unsigned s_c = sbase + (unsigned)(e2.x >> 32), s_left = sbase + (unsigned)e2.y, s_right = sbase + (unsigned)(e2.y >> 32);
+        const bool push_lo = A.slab_on && tl == 0 && A.push_tag, push_hi = A.slab_on && tl == A.nt - 1 && A.push_tag;
+        unsigned Tl, Th;
+        {
+            const u64 s = (e0.x * H.s_cta + H.scg * e0.y + e1.x) & LCG_MASK;  // the table jump over thr_off draws
+            const u64 T = s + TWO31;
+            Tl = (unsigned)T;
+            Th = (unsigned)(T >> 32);
+        }
+        u64 ck = H.ck + e1.y;
+        u64 c1 = H.c1 + LCG_A * thr_off;
+        u64 c2 = H.c2 + LCG_BETA * thr_off;
+        const float m2 = (float)(A.m2_chain ? A.m2_chain[chain] : A.m2);
+        const float lam = (float)(A.lam_chain ? A.lam_chain[chain] : A.lam);
+        const pair_t K_lam = pk(lam, lam), K_m2 = pk(m2, m2);
+        (void)K_lam; (void)K_m2;
+        pair_t ACC1 = 0, ACC2 = 0;
+
+        auto pass = [&](const unsigned kb, const unsigned k) {
+            ulonglong2 U2, D2, TP, TM;
+            if (NDIM >= 4) {
+                U2 = ldg128(p_u2 + kb);
+                D2 = ldg128(p_d2 + kb);
+            }
+            TP = ldg128(p_tp + kb);
+            TM = ldg128(p_tm + kb);
+            // ---- noise phase: W draws in t2 form, Box-Muller ------------------------------------------------
+            const unsigned T0l = Tl, T0h = Th;
+            unsigned tl_ = Tl, th_ = Th, um = 0xFFFFFFFFu;
+            pair_t NZ[NP];
+#pragma unroll
+            for (unsigned q = 0; q < NP; ++q) {
+                unsigned u1a, u2a, u1b, u2b, al, ah, bl, bh;
+                mad48t(tl_, th_, A_LO, A_HI, c1, al, ah);
+                mad48t(tl_, th_, ALPHA_LO32T, ALPHA_HI32T, c2, bl, bh);
+                u1a = __funnelshift_r(al, ah, 16);
+                u2a = __funnelshift_r(bl, bh, 16);
+                c1 += LCG_A;
+                c2 += LCG_BETA;
+                mad48t(bl, bh, A_LO, A_HI, c1, al, ah);
+                mad48t(bl, bh, ALPHA_LO32T, ALPHA_HI32T, c2, tl_, th_);
+                u1b = __funnelshift_r(al, ah, 16);
+                u2b = __funnelshift_r(tl_, th_, 16);
+                if (q + 1 < NP) {
+                    c1 += LCG_A;
+                    c2 += LCG_BETA;
+                } else {  // on to the first site of the next row
+                    c1 += A.t_dc1;
+                    c2 += A.t_dc2;
+                }
+                um = min(min(um, u1a), u2a);  // u1 == 0 (retry) or u2 < 2^15 (`seed+=`) => um < 2^15
+                um = min(min(um, u1b), u2b);
+                if (MATH == 1) {
+                    float l1a, l1b, ta, tb, tha, thb;
+                    upk(mul2(pk(__uint2float_rn(u1a), __uint2float_rn(u1b)), K_2m32), l1a, l1b);
+                    upk(mul2(pk(lg2_approx(l1a), lg2_approx(l1b)), K_k2), ta, tb);
+                    upk(fma2(pk(__uint2float_rn(u2a), __uint2float_rn(u2b)), K_th, K_mpi), tha, thb);
+                    NZ[q] = mul2(pk(__cosf(tha), __cosf(thb)), pk(sqrt_approx(fabsf(ta)), sqrt_approx(fabsf(tb))));
+                } else {
+                    const float da = (float)__dmul_rn(A.nscale, noise_accurate((u64)u1a << 16, (u64)u2a << 16));
+                    const float db = (float)__dmul_rn(A.nscale, noise_accurate((u64)u1b << 16, (u64)u2b << 16));
+                    NZ[q] = pk(-da, -db);
+                }
+            }
+            {   // next row: same x0, L0 draws further
+                mad48t(T0l, T0h, aDl, aDh, ck, Tl, Th);
+                ck += A.t_dck;
+            }
+            // ---- stencil phase ------------------------------------------------------------------------------------
+            pair_t C[NP], U1[NP], D1[NP];
+            {
+                const ulonglong2 c = lds128(s_c + kb), u = lds128(s_c + kb + ROWB), d = lds128(s_c + kb - ROWB);
+                C[0] = c.x; C[1] = c.y;
+                U1[0] = u.x; U1[1] = u.y;
+                D1[0] = d.x; D1[1] = d.y;
+            }
+            const float left = lds32(s_left + kb), right = lds32(s_right + kb);
+            float p[W];
+#pragma unroll
+            for (unsigned q = 0; q < NP; ++q) upk(C[q], p[2 * q], p[2 * q + 1]);
+            pair_t V[NP];
+            float amax = 0.f;
+#pragma unroll
+            for (unsigned q = 0; q < NP; ++q) {
+                const float xm0 = (q == 0) ? left : p[(2 * q + W - 1) % W], xp1 = (q == NP - 1) ? right : p[(2 * q + 2) % W];
+                pair_t Sq = pk(__fadd_rn(p[2 * q + 1], xm0), __fadd_rn(xp1, p[2 * q]));  // phi(+0) + phi(-0)
+                Sq = add2(Sq, U1[q]);
+                Sq = add2(Sq, D1[q]);
+                if (NDIM >= 4) {
+                    Sq = add2(Sq, (q & 1) ? U2.y : U2.x);
+                    Sq = add2(Sq, (q & 1) ? D2.y : D2.x);
+                }
+                Sq = add2(Sq, (q & 1) ? TP.y : TP.x);
+                Sq = add2(Sq, (q & 1) ? TM.y : TM.x);
+                pair_t v = fma2(K_clap, fma2(K_m2d, C[q], Sq), C[q]);
+                if (POT == 4) v = fma2(K_mcdt, mul2(C[q], fma2(K_lam, mul2(C[q], C[q]), K_m2)), v);
+                else v = fma2(K_m2cdt, C[q], v);  // (-c_dt)(2 phi) == (-2 c_dt) phi exactly
+                v = fma2(K_m1, NZ[q], v);          // v + dw, one rounding
+                V[q] = v;
+                float a0, a1;
+                upk(v, a0, a1);
+                amax = fmaxf(fmaxf(fabsf(a0), fabsf(a1)), amax);
+                ACC1 = add2(ACC1, C[q]);           // observables of the pre-update field
+                ACC2 = fma2(C[q], C[q], ACC2);
+            }
+            // clamp (tau_kernel.cl:122-132) and RNG events: one test per strip for both rare cases
+            if (__builtin_expect(!(amax < 1000.0f) | (um < 32768u), 0)) {
+                bool replayed = false;  // an event in this strip: the launch is redone, its clamp hits are not counted
+                if (um < 32768u) {
+                    const u64 z0 = ((((u64)T0h << 32) | T0l) - TWO31) & LCG_MASK;
+                    replayed = strip_events_cold(A.event_key, A.step_index, chain, z0, H.g_cta + thr_off + k * L0, (int)W);
+                }
+                float v0, v1, v2, v3;
+                upk(V[0], v0, v1);
+                upk(V[1], v2, v3);
+                const Clamped cl = clamp_cold(v0, v1, v2, v3);
+                V[0] = pk(cl.v[0], cl.v[1]);
+                V[1] = pk(cl.v[2], cl.v[3]);
+                if (!replayed) nclamp += cl.n;
+            }
+            *reinterpret_cast<ulonglong2 *>(p_dst + kb) = make_ulonglong2(V[0], V[1]);
+            if (__builtin_expect(push_lo | push_hi, 0)) {  // CTA-uniform: boundary slices of a slab ring only
+                const size_t oo = (size_t)(H.o_cta + thr_off + k * L0) * 4u;
+                if (push_lo) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[0] + oo) = make_ulonglong2(V[0], V[1]);
+                if (push_hi) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[1] + oo) = make_ulonglong2(V[0], V[1]);
+            }
+        };
+
+        // ---- the thread's R strips: 4 passes per trip (pass offsets are immediates), then the stream bases move on ----
+#pragma unroll 1
+        for (unsigned k0 = 0; k0 < R; k0 += 4u) {
+#pragma unroll
+            for (unsigned u = 0; u < 4u; ++u) pass(u * ROWB, k0 + u);
+            p_tp += 4u * ROWB;
+            p_tm += 4u * ROWB;
+            if (NDIM >= 4) {
+                p_u2 += 4u * ROWB;
+                p_d2 += 4u * ROWB;
+            }
+            p_dst += 4u * ROWB;
+            asm volatile("" : "+l"(p_tp), "+l"(p_tm), "+l"(p_u2), "+l"(p_d2), "+l"(p_dst));
+            s_c += 4u * ROWB;
+            s_left += 4u * ROWB;
+            s_right += 4u * ROWB;
+        }
+
+        // ---- the omega work-item's draw (gid = V) and the step's final seed -------------------------------------
+        if (threadIdx.x == 0 && H.bx == 0 && tl == 0) {
+            const u64 Vg = (u64)A.V;
+            u64 t1, t2;
+            const u64 sv = lcg_apply(A.vol_jump, A.seed_in[chain], 0) & LCG_MASK;
+            lcg_draw(sv, Vg, t1, t2);
+            if (lcg_event(sv & LCG_MASK, t1, t2)) atomicMin((unsigned long long *)A.event_key, event_key(A.step_index, chain, Vg));
+            A.seed_out[chain] = lcg_next_seed(t2);
+        }
+        // ---- the warp's share of the tile's observable partial; the warp leaves the stage ---------------------------
+        if (A.partials) {
+            float a1l, a1h, a2l, a2h;
+            upk(ACC1, a1l, a1h);
+            upk(ACC2, a2l, a2h);
+            const double a1 = warp_sum((double)a1l + (double)a1h), a2 = warp_sum((double)a2l + (double)a2h);
+            if (lane == 0) { S.red[st][0][warp] = a1; S.red[st][1][warp] = a2; }
+        }
+        __syncwarp();
+        if (lane == 0) tile_mbar_arrive(smem0 + 16u + 8u * st);
+    }
+    if (nclamp) atomicAdd(A.nclamped, (unsigned long long)nclamp);
+}
+
+// SQ_PTILE=0 in the environment: the one-tile-per-CTA kernel (A/B knob); default: the persistent two-stage kernel
+static bool ptile_on() {
+    static const bool on = !(getenv("SQ_PTILE") && atoi(getenv("SQ_PTILE")) == 0);
+    return on;
+}
+// bytes of one staged tile: [halo | rows | halo] per run of rows inside a plane
+static size_t tile_stage_bytes(int L0, int L1, int tpr_log, int R) {
     const unsigned rows_per_cta = (256u >> tpr_log) * (unsigned)R;
     const unsigned seg_rows = rows_per_cta < (unsigned)L1 ? rows_per_cta : (unsigned)L1, nseg = rows_per_cta / seg_rows;
-    return 128 + (size_t)nseg * (seg_rows + 2u) * (size_t)L0 * 4u;
+    return (size_t)nseg * (seg_rows + 2u) * (size_t)L0 * 4u;
+}
+// shared memory a CTA needs: one line of mbarriers + its stage(s)
+size_t tile_smem_bytes(int L0, int L1, int tpr_log, int R) {
+    const size_t stage = tile_stage_bytes(L0, L1, tpr_log, R);
+    return ptile_on() ? 128 + 2 * ((stage + 127) / 128 * 128) : 128 + stage;
 }
 // the tile must be a whole number of planes or divide one (runs of rows never straddle a plane edge); tpr_log = log2 of the
-// threads per row (row length / sites per strip)
+// threads per row (row length / sites per strip).  Three CTAs per SM: 72 KB each.
 bool tile_shape_ok(int L0, int L1, int tpr_log, int R) {
     const unsigned rows_per_cta = (256u >> tpr_log) * (unsigned)R;
     if (L1 % R != 0 || R % 4 != 0) return false;
@@ -463,6 +897,24 @@ bool tile_shape_ok(int L0, int L1, int tpr_log, int R) {
 // which shares this kernel's tiles and jump tables.)
 template <int MATH, int NDIM, int POT, int L0T>
 static cudaError_t tile_go(const LatticeArgs &A, dim3 grid, size_t smem, cudaStream_t st) {
+    if (ptile_on()) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        auto kern = lattice_ptile_kernel<MATH, NDIM, POT, L0T>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 288, smem)) != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        const unsigned long long nt64 = (unsigned long long)grid.x * grid.y * grid.z;
+        if (nt64 >= (1ull << 31) || !A.tile_ctr) return cudaErrorInvalidValue;
+        const unsigned ntiles = (unsigned)nt64, slots = (unsigned)(sms * per_sm);
+        static const unsigned pf = getenv("SQ_PTILE_PF") ? (unsigned)atoi(getenv("SQ_PTILE_PF")) : 7u;  // tuning knob: L2 prefetch mask
+        unsigned nb = ntiles < slots ? ntiles : slots;
+        if (getenv("SQ_DEBUG")) fprintf(stderr, "ptile: sms %d per_sm %d ntiles %u grid %u smem %zu\n", sms, per_sm, ntiles, nb, smem);
+        kern<<<nb, 288, smem, st>>>(A, ntiles, grid.x, (unsigned)((smem - 128) / 2), pf);
+        return cudaGetLastError();
+    }
     if (smem > 48 * 1024) {  // (idempotent; the attribute is per function)
         cudaError_t e = cudaFuncSetAttribute(lattice_tile_kernel<MATH, NDIM, POT, L0T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
         if (e != cudaSuccess) return e;
