@@ -105,7 +105,7 @@ extern "C" void sq_free(sq_ctx *c) {
                     c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps, c->c_ctl, c->c_log_rec, c->c_log_xavg,
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
                     c->l_event, c->l_rebase, c->l_partials, c->l_partials2, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
-                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_nclamp_step, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump, c->l_tile_thr, c->l_tile_ctr,
+                    c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_nclamp_step, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump, c->l_tile_thr, c->l_rows_thr, c->l_tile_ctr,
                     c->r_halo, c->r_error, c->r_progress, c->r_ckpt, c->r_hist_rows, c->r_step_sums, c->r_nclamp_slots};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -219,7 +219,7 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
             while ((1 << tlog) < tpr) tlog++;
             for (int R = force_R ? force_R : 16; R >= 1; R >>= 1) {
                 if (L1 % R != 0 || nrows % (rg * R) != 0 || nrows / (rg * R) > 65535) continue;
-                if (tile && !tile_shape_ok((int)L0, (int)L1, tlog, R)) continue;
+                if (tile && !tile_shape_ok(p.ndim, (int)L0, (int)L1, tlog, R)) continue;
                 const int64_t ctas = nrows / (rg * R) * c->nt * p.nchains;
                 best = R;  // the largest that fits, unless a smaller one is needed to fill the GPU
                 best_w = w;
@@ -307,6 +307,23 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
                 CK(cudaMemset(c->l_tile_ctr, 0, 2 * sizeof(unsigned)));
                 CK(cudaMalloc((void **)&c->l_tile_thr, sizeof(TileThread) * tt.size()));
                 CK(cudaMemcpy(c->l_tile_thr, tt.data(), sizeof(TileThread) * tt.size(), cudaMemcpyHostToDevice));
+                // row-block kernel: thread (tx, ty) owns row ty of every pass; a stage is [halo | RPP rows | halo | t+1 | t-1 | x2+1 | x2-1]
+                const JumpEntry passj = jump_entry(1024);
+                for (u64 t = 0; t < 256; ++t) {
+                    const u64 tx = t % tpr, ty = t / tpr, x0 = tx * w, off = ty * L0 + x0, s_row = (1 + ty) * rowb;
+                    const JumpEntry j = jump_entry(off);
+                    TileThread &e = tt[t];
+                    e = TileThread{};
+                    e.a = j.a; e.g0 = j.g0; e.bg1 = j.bg1;
+                    e.ck_off = LCG_BETA * off * passj.g0;
+                    e.thr_off = (unsigned)off;
+                    e.s_c = (unsigned)(s_row + x0 * 4);
+                    e.s_left = (unsigned)(s_row + (x0 == 0 ? (L0 - 1) * 4 : x0 * 4 - 4));
+                    e.s_right = (unsigned)(s_row + (x0 + w == L0 ? 0 : (x0 + w) * 4));
+                    e.row = (unsigned)ty;
+                }
+                CK(cudaMalloc((void **)&c->l_rows_thr, sizeof(TileThread) * tt.size()));
+                CK(cudaMemcpy(c->l_rows_thr, tt.data(), sizeof(TileThread) * tt.size(), cudaMemcpyHostToDevice));
             }
 
         }
@@ -497,6 +514,11 @@ LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */
     A.thr_jump = c->l_thr_jump;
     A.tile_thr = c->l_tile_thr;
     A.tile_ctr = c->l_tile_ctr;
+    A.rows_thr = c->l_rows_thr;
+    A.prow_jump = jump_entry(1024);
+    A.p_dck = LCG_BETA * 1024ULL * A.prow_jump.g0;
+    A.p_dc1 = (1024ULL - 3) * LCG_A;
+    A.p_dc2 = (1024ULL - 3) * LCG_BETA;
     A.row_jump = jump_entry((u64)p.dims[0]);
     A.rebase = c->l_rebase;
     sq_fill_rebase_inline(A, nullptr, 0);

@@ -82,7 +82,7 @@ struct sq_ctx {
     int m_R = 0, m_tpr_log = 0, m_w = 4;
     JumpEntry *l_cta_jump = nullptr, *l_thr_jump = nullptr;
     unsigned *l_tile_ctr = nullptr;    // [2] persistent tile kernel's claim counters
-    sq::TileThread *l_tile_thr = nullptr;  // [256] tile kernel: a thread's place inside any tile
+    sq::TileThread *l_tile_thr = nullptr, *l_rows_thr = nullptr;  // [256] tile kernel: a thread's place inside any tile
     // resident 2-D path (sq_resident.cu)
     bool res_ok = false;
     int res_nb = 0, res_rows = 0;

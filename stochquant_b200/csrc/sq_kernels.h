@@ -128,7 +128,10 @@ struct LatticeArgs {
     const JumpEntry *cta_jump;   // [ctas per slice] jump over bx * rows_per_cta * L0 draws
     const JumpEntry *thr_jump;   // [256] jump over (ty * R * L0 + tx * m_w) draws
     const TileThread *tile_thr;  // [256] tile kernel (null unless m_on == 2)
-    unsigned *tile_ctr;          // [2] persistent tile kernel: next tile to claim, CTAs that have finished (both 0 between launches)
+    unsigned *tile_ctr;          // [2] row-block kernel: next tile to claim, CTAs that have finished (both 0 between launches)
+    const TileThread *rows_thr;  // [256] row-block kernel: thread (tx, ty) = row ty of a pass, sites 4 tx ..
+    JumpEntry prow_jump;         // jump over 1024 draws (one pass down at the same place in the block)
+    u64 p_dck, p_dc1, p_dc2;     // row-block kernel: per-pass increments of the affine constant and of the two site constants
     JumpEntry row_jump;          // jump over L0 draws (one row down at fixed x0)
     u64 t_dck, t_dc1, t_dc2;     // tile kernel: per-row increments of the affine constant and of the two site constants
     // ---- multi-GPU slab ring (sq_slab.cu); slab_on == 0: everything below is unused ----------
@@ -148,8 +151,8 @@ cudaError_t preload_lattice_step(int real, int math, int ndim);
 cudaError_t launch_lattice_march(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream);
 // sq_tile.cu: the same tiles staged through shared memory by bulk asynchronous copies (LatticeArgs::m_on == 2)
 cudaError_t launch_lattice_tile(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream);
-bool tile_shape_ok(int L0, int L1, int tpr_log, int R);
-size_t tile_smem_bytes(int L0, int L1, int tpr_log, int R);
+bool tile_shape_ok(int ndim, int L0, int L1, int tpr_log, int R);
+size_t tile_smem_bytes(int ndim, int L0, int L1, int tpr_log, int R);
 
 struct FinalizeArgs {
     int nt, nchains, ctas_per_slice;

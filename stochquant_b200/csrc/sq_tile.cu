@@ -447,28 +447,38 @@ __global__ void __launch_bounds__(256, NP == 4 ? 2 : TILE_MINB) lattice_tile_ker
 }
 
 // =====================================================================================================================
-// Persistent form: one CTA per slot of the GPU (3 per SM), each working through tiles in TWO shared-memory stages.  What a
-// CTA of the one-tile kernel spends before its first strip -- header, copy issue, a DRAM round trip: about a fifth of its
-// life on 64^4, with a third of the SM's warps parked meanwhile -- is done for the next tile while this one is computed:
-//   * full[s] / empty[s] mbarriers per stage: the producer arms full[s] with the byte count and issues the bulk copies; the
-//     256 computing threads wait on it, compute, and each warp's lane 0 arrives on empty[s] (count 8);
-//   * the producer is a ninth warp: it waits for empty[s] (everybody has left the tile before last), writes that tile's
-//     observable partial and slab-ring flag, CLAIMS the next tile from a counter, computes its header, issues its copies and
-//     asks L2 for its share of the four streams that are read straight from global memory -- up to two tiles ahead of use;
-//   * no CTA-wide barrier after the first.
-// Tiles are claimed in order, as stages come free -- what the hardware does with CTAs -- so the tiles in flight stay one
-// contiguous window of the one-tile kernel's CTA order (cta_slice_position: L2 chunks swept through the time slices, a slab
-// ring's boundary slices first; chains outermost).  Partials, clamp slots and jump tables are unchanged.
-// Measured dead ends, 256^3 x 32 slices, one-tile kernel = 384 G site-updates/s:
-//   - a FIXED stride (tile = blockIdx.x + i gridDim.x): 209.  The CTAs drift apart over their ~150 tiles, the L2 chunk order
-//     then means nothing and every site comes from HBM three times (6.6 GB read per step instead of 2.6, ncu);
-//   - the producer role rotating over the eight computing warps instead of a ninth warp: 219 (same drift, and whoever
-//     produces falls behind by the header's latency -- the next producer has to wait for exactly that warp).
-struct PTileShared {
-    TileHdr H[2];
+// Row-block streaming form (the default): every operand of the stencil comes from shared memory, staged a PASS at a time.
+//
+// A pass = the 1024 sites all 256 computing threads update at once = RPP = 1024 / L0 consecutive rows of a slice (thread
+// (tx, ty): row ty of the block, sites 4 tx .. 4 tx + 3).  What a pass reads is seven linear runs of global memory:
+//   the RPP rows themselves + the row before + the row after (x1 -+ 1, wrapped inside the plane), and the same RPP rows of
+//   the slice above, the slice below, the plane above and the plane below (t +- 1, x2 +- 1)
+// -- seven cp.async.bulk copies into one STAGE of (5 RPP + 2) rows, about 21 KB.  Three stages per CTA, three CTAs per SM:
+// ~190 KB of loads in flight per SM, against the 48 KB the 24 warps' own 128-bit loads could keep in flight (four per
+// warp and pass) -- that was the one-tile kernel's limit: a third of its stall samples sat on the first use of those loads
+// (profiles/r02_slab_tile.txt), Little's law at ~1 us of loaded latency.
+//   * full[s] / empty[s] mbarriers per stage; a ninth warp produces: waits for empty[s] (count 8: lane 0 of every
+//     computing warp), arms full[s] with the stage's byte count, seven lanes issue one copy each;
+//   * the eight computing warps run the noise phase of a pass (2/3 of its instructions, no field data) BEFORE they wait
+//     for its stage; then seven 128-bit and two 32-bit shared-memory loads, the update, one 128-bit global store;
+//   * tiles (R passes = what the marching kernel calls a CTA's rows: partials, jump tables and clamp slots are shared with
+//     it) are CLAIMED from a counter, in order, by the producer -- what the hardware does with CTAs -- so the tiles in
+//     flight stay one contiguous window of the L2 chunk order (cta_slice_position).  The chain state is set from the
+//     tile's header (written by the producer before it arms the first stage of the tile) and walked affinely from pass
+//     to pass; no CTA-wide barrier after the first.
+// Measured dead ends on the way (256^3 x 32 slices; one-tile kernel = 384 G site-updates/s):
+//   - whole tiles in two stages, FIXED stride (tile = blockIdx.x + i gridDim.x): 209.  The CTAs drift apart over their
+//     ~150 tiles, the L2 chunk order then means nothing and every site comes from HBM three times (6.6 GB read per step
+//     instead of 2.6, ncu);
+//   - the producer role rotating over the eight computing warps instead of a ninth warp: 219;
+//   - whole tiles in two stages, claimed dynamically, t+-1 / x2+-1 still direct loads: 347 -- hiding the CTA start-up
+//     buys nothing while the direct loads bound the passes.
+constexpr unsigned ROWS_D = 3;  // stages
+struct RowsShared {
+    TileHdr H[2];          // by tile parity
     double red[2][2][8];
     int chain[2];
-    int end[2];   // the stage holds no tile: the grid has run out of them
+    int end[2];            // no tile: the grid has run out of them
     int skip;
 };
 
@@ -477,37 +487,44 @@ __device__ __forceinline__ void tile_mbar_arrive(unsigned bar) {
 }
 
 template <int MATH, int NDIM, int POT, int L0T>
-__global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs A, const unsigned ntiles, const unsigned cps, const unsigned stage_stride, const unsigned pf) {
+__global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs A, const unsigned ntiles, const unsigned cps, const unsigned stage_stride) {
     constexpr unsigned NP = 2, W = 4;
+    constexpr unsigned NSTREAM = (NDIM >= 4) ? 5u : 3u;
     extern __shared__ __align__(128) unsigned char tile_smem[];
-    __shared__ PTileShared S;
+    __shared__ RowsShared S;
     const unsigned L0 = L0T ? (unsigned)L0T : (unsigned)A.dim[0], L1 = (unsigned)A.dim[1];
     const unsigned L2 = (NDIM >= 4) ? (unsigned)A.dim[2] : 1u;
     const unsigned ROWB = L0 * 4u;
-    const unsigned R = (unsigned)A.m_R;
-    const unsigned rows_per_cta = (256u >> A.m_tpr_log) * R;
+    const unsigned RPP = 256u >> A.m_tpr_log;   // rows per pass
+    const unsigned R = (unsigned)A.m_R;         // passes per tile
+    constexpr unsigned PASSB = 4096u;           // RPP * ROWB: bytes of one stream in a stage
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(tile_smem);
-    // mbarriers: full[0], full[1], empty[0], empty[1] at smem0 + 0 / 8 / 16 / 24 ; stage s data at smem0 + 128 + s * stage_stride
+    // mbarriers: full[s] at smem0 + 8 s, empty[s] at smem0 + 32 + 8 s ; stage s at smem0 + 128 + s * stage_stride:
+    //   [x1-1 halo row | RPP rows | x1+1 halo row | t+1 rows | t-1 rows | x2+1 rows | x2-1 rows]
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 
     if (threadIdx.x == 0) {
         // an earlier launch flagged an event: this one will be replayed
         S.skip = *((volatile const u64 *)A.event_key) != NO_EVENT;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem0) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem0 + 8u) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem0 + 16u) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem0 + 24u) : "memory");
+        for (unsigned s = 0; s < ROWS_D; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem0 + 8u * s) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem0 + 32u + 8u * s) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (S.skip) return;
 
-    if (warp == 8) {  // ================= the producer warp: up to two tiles ahead of the eight that compute =================
-        // ---- tile `lin` into stage st: header (lane 0), copies and L2 prefetches (all lanes) ----
-        auto produce = [&](unsigned lin, const unsigned st) {
-            TileHdr &H = S.H[st];
+    if (warp == 8) {  // ================= the producer warp =========================================================
+        // ---- claim the next tile and write its header into slot hs (lane 0); false: none left ----
+        auto claim = [&](const unsigned hs) -> bool {
+            unsigned lin = 0;
+            if (lane == 0) lin = atomicAdd(A.tile_ctr, 1u);
+            lin = __shfl_sync(0xFFFFFFFFu, lin, 0);
+            if (lin >= ntiles) return false;
             if (lane == 0) {
-                S.end[st] = 0;
+                TileHdr &H = S.H[hs];
+                S.end[hs] = 0;
                 const unsigned per_chain = cps * (unsigned)A.nt;
                 const unsigned chain = lin / per_chain;
                 lin -= chain * per_chain;
@@ -544,13 +561,14 @@ __global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs
                 }
                 const long long vs = A.vslice;
                 const u64 gslice = (u64)(A.slab_t0 + tl) * (u64)vs;
-                const unsigned o_cta = bx * rows_per_cta * L0;
+                const unsigned o_cta = bx * (RPP * R) * L0;
                 const u64 g_cta = gslice + o_cta;
                 const u64 s_sl = lcg_apply(A.slice_jump[tl], A.seed_in[chain], 0) & LCG_MASK;
                 H.s_cta = lcg_apply(A.cta_jump[bx], s_sl, gslice) & LCG_MASK;
                 const u64 scg = LCG_BETA * g_cta + LCG_GAMMA;
                 H.scg = scg;
-                H.ck = scg * A.row_jump.g0 + A.row_jump.bg1 - A.row_jump.a * TWO31 + TWO31;
+                // T(next pass) = alpha^1024 T + ck ; ck itself is a running sum
+                H.ck = scg * A.prow_jump.g0 + A.prow_jump.bg1 - A.prow_jump.a * TWO31 + TWO31;
                 H.c1 = site_const(g_cta) - LCG_A * TWO31;
                 H.c2 = (LCG_A + 1) * site_const(g_cta) - LCG_ALPHA * TWO31;
                 H.g_cta = g_cta;
@@ -559,98 +577,107 @@ __global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs
                 const float *tm = (tl > 0) ? cur - vs : (A.wrap_time ? in + (long long)(A.nt - 1) * vs : (const float *)A.ghost_lo);
                 const float *tp = (tl < A.nt - 1) ? cur + vs : (A.wrap_time ? in : (const float *)A.ghost_hi);
                 H.cur_slice = cur;
-                H.cur = (const char *)(cur + o_cta);
-                H.tp = (const char *)(tp + o_cta);
-                H.tm = (const char *)(tm + o_cta);
+                H.cur = (const char *)cur;   // (slice bases: the producer adds the row)
+                H.tp = (const char *)tp;
+                H.tm = (const char *)tm;
                 H.dst = (char *)((float *)A.out + (long long)chain * A.chain_stride + (long long)tl * vs + o_cta);
                 H.tl = tl;
                 H.bx = bx;
-                H.x2 = (NDIM >= 4) ? (bx * rows_per_cta) / L1 : 0u;
+                H.x2 = 0;
                 H.o_cta = o_cta;
-                S.chain[st] = (int)chain;
+                S.chain[hs] = (int)chain;
             }
             __syncwarp();
-            const unsigned seg_rows = rows_per_cta < L1 ? rows_per_cta : L1, nseg = rows_per_cta / seg_rows;
-            const unsigned seg_bytes = (seg_rows + 2u) * ROWB;
-            const unsigned tile_row0 = H.bx * rows_per_cta;
-            const float *cur = H.cur_slice;
-            const unsigned bar = smem0 + 8u * st, data0 = smem0 + 128u + st * stage_stride;
-            if (lane == 0) tile_expect_tx(bar, nseg * seg_bytes);  // (release: the header is visible to whoever sees the phase end)
+            return true;
+        };
+        // ---- everybody has left the tile in header slot hs: its observable partial, and a slab ring's flag (lane 0) ----
+        auto retire = [&](const unsigned hs) {
+            if (lane == 0) {
+                const TileHdr &H = S.H[hs];
+                const int tl = H.tl, chain = S.chain[hs];
+                if (A.partials) {
+                    double s1 = 0, s2 = 0;
+                    for (int q = 0; q < 8; ++q) { s1 += S.red[hs][0][q]; s2 += S.red[hs][1][q]; }
+                    double *p = A.partials + (((long long)chain * A.nt + tl) * cps + H.bx) * 2;
+                    p[0] = s1;
+                    p[1] = s2;
+                }
+                const bool push_lo = A.slab_on && tl == 0 && A.push_tag, push_hi = A.slab_on && tl == A.nt - 1 && A.push_tag;
+                if (push_lo || push_hi) {  // last tile of the slice: everything is out, raise the neighbour's flag
+                    __threadfence_system();
+                    if (push_lo && atomicAdd(A.push_count + 0, 1u) == cps - 1) {
+                        A.push_count[0] = 0;
+                        __threadfence_system();
+                        st_release_sys_u32(A.push_flag[0], A.push_tag);
+                    }
+                    if (push_hi && atomicAdd(A.push_count + 1, 1u) == cps - 1) {
+                        A.push_count[1] = 0;
+                        __threadfence_system();
+                        st_release_sys_u32(A.push_flag[1], A.push_tag);
+                    }
+                }
+            }
             __syncwarp();
-            for (unsigned c = lane; c < 3u * nseg; c += 32u) {
-                const unsigned sg = c / 3u, part = c - 3u * sg;            // 0 rows, 1 halo below, 2 halo above
-                const unsigned row0 = tile_row0 + sg * seg_rows;            // first row of the run (row index inside the slice)
-                const unsigned x1a = row0 % L1, prow0 = row0 - x1a;         // its x1, first row of its plane
-                unsigned src_row, dst_off, bytes;
-                if (part == 0) { src_row = row0; dst_off = ROWB; bytes = seg_rows * ROWB; }
-                else if (part == 1) { src_row = (x1a == 0) ? prow0 + L1 - 1u : row0 - 1u; dst_off = 0; bytes = ROWB; }
-                else { src_row = (x1a + seg_rows == L1) ? prow0 : row0 + seg_rows; dst_off = (seg_rows + 1u) * ROWB; bytes = ROWB; }
-                bulk_g2s(data0 + sg * seg_bytes + dst_off, cur + (size_t)src_row * L0, bytes, bar);
-            }
-            if (lane == 30 && (pf & 1u)) bulk_prefetch_l2(H.tp, rows_per_cta * ROWB);
-            if (lane == 31 && (pf & 2u)) bulk_prefetch_l2(H.tm, rows_per_cta * ROWB);
-            if (NDIM >= 4 && (pf & 4u)) {
-                const long long planeR = (long long)L0 * L1, wrapR = (long long)(L2 - 1) * planeR;
-                for (unsigned c = lane; c < 2u * nseg; c += 32u) {
-                    const unsigned sg = c >> 1, row0 = tile_row0 + sg * seg_rows, x2s = row0 / L1;
-                    const float *base = cur + (size_t)row0 * L0;
-                    const float *q = (c & 1) ? base + ((x2s == 0) ? wrapR : -planeR) : base + ((x2s + 1 == L2) ? -wrapR : planeR);
-                    bulk_prefetch_l2(q, seg_rows * ROWB);
-                }
-            }
         };
-        // ---- everybody has left the tile in stage st: its observable partial, and a slab ring's flag (lane 0) ----
-        auto retire = [&](const unsigned st) {
-            if (lane != 0) return;
-            const TileHdr &H = S.H[st];
-            const int tl = H.tl, chain = S.chain[st];
-            if (A.partials) {
-                double s1 = 0, s2 = 0;
-                for (int q = 0; q < 8; ++q) { s1 += S.red[st][0][q]; s2 += S.red[st][1][q]; }
-                double *p = A.partials + (((long long)chain * A.nt + tl) * cps + H.bx) * 2;
-                p[0] = s1;
-                p[1] = s2;
-            }
-            const bool push_lo = A.slab_on && tl == 0 && A.push_tag, push_hi = A.slab_on && tl == A.nt - 1 && A.push_tag;
-            if (push_lo || push_hi) {  // last tile of the slice: everything is out, raise the neighbour's flag
-                __threadfence_system();
-                if (push_lo && atomicAdd(A.push_count + 0, 1u) == cps - 1) {
-                    A.push_count[0] = 0;
-                    __threadfence_system();
-                    st_release_sys_u32(A.push_flag[0], A.push_tag);
-                }
-                if (push_hi && atomicAdd(A.push_count + 1, 1u) == cps - 1) {
-                    A.push_count[1] = 0;
-                    __threadfence_system();
-                    st_release_sys_u32(A.push_flag[1], A.push_tag);
-                }
-            }
-        };
-        unsigned n = 0;
-#pragma unroll 1
-        for (;;) {
-            const unsigned st = n & 1u;
-            if (n >= 2) {
-                tile_mbar_wait(smem0 + 16u + 8u * st, ((n - 2) >> 1) & 1u);  // everybody has left tile n-2
-                retire(st);
-                __syncwarp();
-            }
-            unsigned lin = 0;
-            if (lane == 0) lin = atomicAdd(A.tile_ctr, 1u);
-            lin = __shfl_sync(0xFFFFFFFFu, lin, 0);
-            if (lin >= ntiles) {
-                if (lane == 0) {
-                    S.end[st] = 1;
-                    tile_mbar_arrive(smem0 + 8u * st);  // (count 1: the phase ends, the eight warps see `end`)
-                }
-                break;
-            }
-            produce(lin, st);
-            ++n;
+        const unsigned stage_bytes = (NSTREAM * RPP + 2u) * ROWB;
+        unsigned stage = 0, phase = 0, g = 0, t = 0;  // stage / phase of pass g ; t: tiles started
+        bool more = claim(0);
+        if (!more && lane == 0) {
+            S.end[0] = 1;
+            tile_mbar_arrive(smem0);
         }
-        if (n >= 1) {  // the last tile's partial and flag
-            tile_mbar_wait(smem0 + 16u + 8u * ((n - 1) & 1u), ((n - 1) >> 1) & 1u);
-            retire((n - 1) & 1u);
+#pragma unroll 1
+        while (more) {
+            const TileHdr &H = S.H[t & 1u];
+            // lane roles: 0 rows, 1 row before, 2 row after, 3 slice above, 4 slice below, 5 plane above, 6 plane below
+            const char *base = (lane == 3) ? H.tp : (lane == 4 ? H.tm : H.cur);
+            const unsigned row0 = H.bx * (RPP * R);
+            unsigned x1a = row0 % L1, x2 = (NDIM >= 4) ? row0 / L1 : 0u;
+            const unsigned dst_row = lane == 0 ? 1u : (lane == 1 ? 0u : (lane == 2 ? RPP + 1u : (lane - 2u) * RPP + 2u));
+            const unsigned bytes = (lane == 1 || lane == 2) ? ROWB : PASSB;
+            const bool active = lane < NSTREAM + 2u;
+#pragma unroll 1
+            for (unsigned p = 0; p < R; ++p) {
+                if (g >= ROWS_D) {
+                    tile_mbar_wait(smem0 + 32u + 8u * stage, phase ^ 1u);  // everybody has left pass g - D
+                    // ... if that was the first pass of this tile, every warp has written its share of the tile before's partial
+                    if (p == ROWS_D && t >= 1) retire((t - 1u) & 1u);
+                }
+                long long off = 0;  // rows, relative to the block's first row
+                if (lane == 1) off = (x1a == 0) ? (long long)L1 - 1 : -1;
+                if (lane == 2) off = (x1a + RPP == L1) ? (long long)RPP - (long long)L1 : (long long)RPP;
+                if (NDIM >= 4) {
+                    if (lane == 5) off = (x2 + 1 == L2) ? -(long long)(L2 - 1) * L1 : (long long)L1;
+                    if (lane == 6) off = (x2 == 0) ? (long long)(L2 - 1) * L1 : -(long long)L1;
+                }
+                const unsigned bar = smem0 + 8u * stage;
+                if (lane == 0) tile_expect_tx(bar, stage_bytes);  // (release: a new tile's header is visible to whoever sees the phase end)
+                __syncwarp();
+                if (active) bulk_g2s(smem0 + 128u + stage * stage_stride + dst_row * ROWB, base + ((long long)(row0 + p * RPP) + off) * (long long)ROWB, bytes, bar);
+                x1a += RPP;
+                if (x1a == L1) {
+                    x1a = 0;
+                    ++x2;
+                }
+                ++g;
+                if (++stage == ROWS_D) {
+                    stage = 0;
+                    phase ^= 1u;
+                }
+            }
+            ++t;
+            more = claim(t & 1u);
+            if (!more) {  // tell the computing warps: the next pass's stage carries `end` instead of data
+                if (g >= ROWS_D) tile_mbar_wait(smem0 + 32u + 8u * stage, phase ^ 1u);
+                if (lane == 0) {
+                    S.end[t & 1u] = 1;
+                    tile_mbar_arrive(smem0 + 8u * stage);
+                }
+            }
+        }
+        if (t >= 1) {  // the last tile's partial and flag: the computing warps arrive once more when they see `end`
+            tile_mbar_wait(smem0 + 32u + 8u * stage, phase);
+            retire((t - 1u) & 1u);
         }
         // the last CTA out rearms the counters for the next launch on the stream
         if (lane == 0 && atomicAdd(A.tile_ctr + 1, 1u) == gridDim.x - 1) {
@@ -662,7 +689,7 @@ __global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs
 
     // ================================ the eight computing warps ===================================================
     unsigned nclamp = 0;
-    const unsigned aDl = (unsigned)A.row_jump.a, aDh = (unsigned)(A.row_jump.a >> 32);
+    const unsigned aDl = (unsigned)A.prow_jump.a, aDh = (unsigned)(A.prow_jump.a >> 32);
     const float c_lap = (float)A.c_lap, c_dt = (float)A.c_dt;
     const pair_t K_m2d = pk(-(float)(2 * NDIM), -(float)(2 * NDIM)), K_clap = pk(c_lap, c_lap);
     const pair_t K_m2cdt = pk(-2.0f * c_dt, -2.0f * c_dt), K_mcdt = pk(-c_dt, -c_dt), K_m1 = pk(-1.0f, -1.0f);
@@ -670,44 +697,35 @@ __global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs
     const float kth = (float)(2.0 * 3.1415 / 4294967296.0);  // theta - pi = 2*3.1415 v2 - pi, v2 = (float)u2 * 2^-32
     const pair_t K_th = pk(kth, kth), K_mpi = pk(-3.14159265358979f, -3.14159265358979f);
     (void)K_m2cdt; (void)K_mcdt; (void)K_2m32; (void)K_k2; (void)K_th; (void)K_mpi;
-    const char *te = (const char *)(A.tile_thr + threadIdx.x);
+    // the thread's place inside a pass: one table entry, for the whole kernel
+    const TileThread &E = A.rows_thr[threadIdx.x];
+    const unsigned thr_off = E.thr_off;                       // ty L0 + 4 tx
+    const unsigned o_c = 128u + E.s_c, o_left = 128u + E.s_left, o_right = 128u + E.s_right;  // byte offsets inside a stage (+ the barrier line)
+    const u64 e_a = E.a, e_g0 = E.g0, e_bg1 = E.bg1, e_ck = E.ck_off;
+    unsigned stage = 0, phase = 0;
 
 #pragma unroll 1
-    for (unsigned i = 0;; ++i) {
-        const unsigned st = i & 1u;
-        // the thread's place inside a tile: one 64-byte table entry (L1-resident after the first tile)
-        const ulonglong2 e0 = ldg128(te), e1 = ldg128(te + 16), e2 = ldg128(te + 32);
-        unsigned e_plane = 0;
-        if (NDIM >= 4) e_plane = A.tile_thr[threadIdx.x].plane;
-        tile_mbar_wait(smem0 + 8u * st, (i >> 1) & 1u);  // header written, tile landed
-        if (S.end[st]) break;
-        const TileHdr &H = S.H[st];
-        const int chain = S.chain[st];
-        const int tl = H.tl;
-
-        // ---- the thread's first strip: stream bases, staged-tile addresses, chain state ---------------------------
-        const unsigned thr_off = (unsigned)e2.x;
-        const u64 bo = (u64)thr_off * 4u;
-        const char *p_tp = H.tp + bo, *p_tm = H.tm + bo;
-        const char *p_u2 = nullptr, *p_d2 = nullptr;
-        if (NDIM >= 4) {
-            const unsigned x2 = H.x2 + e_plane;
-            const long long planeB = (long long)L0 * L1 * 4, wrapB = (long long)(L2 - 1) * planeB;
-            p_u2 = H.cur + bo + ((x2 + 1 == L2) ? -wrapB : planeB);
-            p_d2 = H.cur + bo + ((x2 == 0) ? wrapB : -planeB);
+    for (unsigned t = 0;; ++t) {
+        const unsigned hs = t & 1u;
+        tile_mbar_wait(smem0 + 8u * stage, phase);  // the tile's first stage: header written (and the rows landed)
+        if (S.end[hs]) {  // (one more arrival: the producer then knows the last tile's partial is complete)
+            __syncwarp();
+            if (lane == 0) tile_mbar_arrive(smem0 + 32u + 8u * stage);
+            break;
         }
-        char *p_dst = H.dst + bo;
-        const unsigned sbase = smem0 + st * stage_stride;
-        unsigned s_c = sbase + (unsigned)(e2.x >> 32), s_left = sbase + (unsigned)e2.y, s_right = sbase + (unsigned)(e2.y >> 32);
+        const TileHdr &H = S.H[hs];
+        const int chain = S.chain[hs];
+        const int tl = H.tl;
+        char *p_dst = H.dst + (u64)thr_off * 4u;
         const bool push_lo = A.slab_on && tl == 0 && A.push_tag, push_hi = A.slab_on && tl == A.nt - 1 && A.push_tag;
         unsigned Tl, Th;
         {
-            const u64 s = (e0.x * H.s_cta + H.scg * e0.y + e1.x) & LCG_MASK;  // the table jump over thr_off draws
+            const u64 s = (e_a * H.s_cta + H.scg * e_g0 + e_bg1) & LCG_MASK;  // the table jump over thr_off draws
             const u64 T = s + TWO31;
             Tl = (unsigned)T;
             Th = (unsigned)(T >> 32);
         }
-        u64 ck = H.ck + e1.y;
+        u64 ck = H.ck + e_ck;
         u64 c1 = H.c1 + LCG_A * thr_off;
         u64 c2 = H.c2 + LCG_BETA * thr_off;
         const float m2 = (float)(A.m2_chain ? A.m2_chain[chain] : A.m2);
@@ -716,15 +734,9 @@ __global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs
         (void)K_lam; (void)K_m2;
         pair_t ACC1 = 0, ACC2 = 0;
 
-        auto pass = [&](const unsigned kb, const unsigned k) {
-            ulonglong2 U2, D2, TP, TM;
-            if (NDIM >= 4) {
-                U2 = ldg128(p_u2 + kb);
-                D2 = ldg128(p_d2 + kb);
-            }
-            TP = ldg128(p_tp + kb);
-            TM = ldg128(p_tm + kb);
-            // ---- noise phase: W draws in t2 form, Box-Muller ------------------------------------------------
+#pragma unroll 1
+        for (unsigned p = 0; p < R; ++p) {
+            // ---- noise phase: W draws in t2 form, Box-Muller (no field data: runs ahead of the stage) ---------------
             const unsigned T0l = Tl, T0h = Th;
             unsigned tl_ = Tl, th_ = Th, um = 0xFFFFFFFFu;
             pair_t NZ[NP];
@@ -744,9 +756,9 @@ __global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs
                 if (q + 1 < NP) {
                     c1 += LCG_A;
                     c2 += LCG_BETA;
-                } else {  // on to the first site of the next row
-                    c1 += A.t_dc1;
-                    c2 += A.t_dc2;
+                } else {  // on to the strip's place in the next pass
+                    c1 += A.p_dc1;
+                    c2 += A.p_dc2;
                 }
                 um = min(min(um, u1a), u2a);  // u1 == 0 (retry) or u2 < 2^15 (`seed+=`) => um < 2^15
                 um = min(min(um, u1b), u2b);
@@ -762,28 +774,37 @@ __global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs
                     NZ[q] = pk(-da, -db);
                 }
             }
-            {   // next row: same x0, L0 draws further
+            {   // next pass: same place in the block, 1024 draws further
                 mad48t(T0l, T0h, aDl, aDh, ck, Tl, Th);
-                ck += A.t_dck;
+                ck += A.p_dck;
             }
-            // ---- stencil phase ------------------------------------------------------------------------------------
+            // ---- stencil phase: everything from the stage ------------------------------------------------------------
+            tile_mbar_wait(smem0 + 8u * stage, phase);
+            const unsigned sb = smem0 + stage * stage_stride;
             pair_t C[NP], U1[NP], D1[NP];
+            ulonglong2 U2, D2, TP, TM;
             {
-                const ulonglong2 c = lds128(s_c + kb), u = lds128(s_c + kb + ROWB), d = lds128(s_c + kb - ROWB);
+                const ulonglong2 c = lds128(sb + o_c), u = lds128(sb + o_c + ROWB), d = lds128(sb + o_c - ROWB);
                 C[0] = c.x; C[1] = c.y;
                 U1[0] = u.x; U1[1] = u.y;
                 D1[0] = d.x; D1[1] = d.y;
             }
-            const float left = lds32(s_left + kb), right = lds32(s_right + kb);
-            float p[W];
+            const float left = lds32(sb + o_left), right = lds32(sb + o_right);
+            TP = lds128(sb + o_c + ROWB + PASSB);
+            TM = lds128(sb + o_c + ROWB + 2u * PASSB);
+            if (NDIM >= 4) {
+                U2 = lds128(sb + o_c + ROWB + 3u * PASSB);
+                D2 = lds128(sb + o_c + ROWB + 4u * PASSB);
+            }
+            float pp[W];
 #pragma unroll
-            for (unsigned q = 0; q < NP; ++q) upk(C[q], p[2 * q], p[2 * q + 1]);
+            for (unsigned q = 0; q < NP; ++q) upk(C[q], pp[2 * q], pp[2 * q + 1]);
             pair_t V[NP];
             float amax = 0.f;
 #pragma unroll
             for (unsigned q = 0; q < NP; ++q) {
-                const float xm0 = (q == 0) ? left : p[(2 * q + W - 1) % W], xp1 = (q == NP - 1) ? right : p[(2 * q + 2) % W];
-                pair_t Sq = pk(__fadd_rn(p[2 * q + 1], xm0), __fadd_rn(xp1, p[2 * q]));  // phi(+0) + phi(-0)
+                const float xm0 = (q == 0) ? left : pp[(2 * q + W - 1) % W], xp1 = (q == NP - 1) ? right : pp[(2 * q + 2) % W];
+                pair_t Sq = pk(__fadd_rn(pp[2 * q + 1], xm0), __fadd_rn(xp1, pp[2 * q]));  // phi(+0) + phi(-0)
                 Sq = add2(Sq, U1[q]);
                 Sq = add2(Sq, D1[q]);
                 if (NDIM >= 4) {
@@ -803,12 +824,19 @@ __global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs
                 ACC1 = add2(ACC1, C[q]);           // observables of the pre-update field
                 ACC2 = fma2(C[q], C[q], ACC2);
             }
+            // the warp has read what it needs from the stage
+            __syncwarp();
+            if (lane == 0) tile_mbar_arrive(smem0 + 32u + 8u * stage);
+            if (++stage == ROWS_D) {
+                stage = 0;
+                phase ^= 1u;
+            }
             // clamp (tau_kernel.cl:122-132) and RNG events: one test per strip for both rare cases
             if (__builtin_expect(!(amax < 1000.0f) | (um < 32768u), 0)) {
                 bool replayed = false;  // an event in this strip: the launch is redone, its clamp hits are not counted
                 if (um < 32768u) {
                     const u64 z0 = ((((u64)T0h << 32) | T0l) - TWO31) & LCG_MASK;
-                    replayed = strip_events_cold(A.event_key, A.step_index, chain, z0, H.g_cta + thr_off + k * L0, (int)W);
+                    replayed = strip_events_cold(A.event_key, A.step_index, chain, z0, H.g_cta + thr_off + p * 1024u, (int)W);
                 }
                 float v0, v1, v2, v3;
                 upk(V[0], v0, v1);
@@ -818,30 +846,13 @@ __global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs
                 V[1] = pk(cl.v[2], cl.v[3]);
                 if (!replayed) nclamp += cl.n;
             }
-            *reinterpret_cast<ulonglong2 *>(p_dst + kb) = make_ulonglong2(V[0], V[1]);
+            *reinterpret_cast<ulonglong2 *>(p_dst) = make_ulonglong2(V[0], V[1]);
             if (__builtin_expect(push_lo | push_hi, 0)) {  // CTA-uniform: boundary slices of a slab ring only
-                const size_t oo = (size_t)(H.o_cta + thr_off + k * L0) * 4u;
+                const size_t oo = (size_t)(H.o_cta + thr_off + p * 1024u) * 4u;
                 if (push_lo) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[0] + oo) = make_ulonglong2(V[0], V[1]);
                 if (push_hi) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[1] + oo) = make_ulonglong2(V[0], V[1]);
             }
-        };
-
-        // ---- the thread's R strips: 4 passes per trip (pass offsets are immediates), then the stream bases move on ----
-#pragma unroll 1
-        for (unsigned k0 = 0; k0 < R; k0 += 4u) {
-#pragma unroll
-            for (unsigned u = 0; u < 4u; ++u) pass(u * ROWB, k0 + u);
-            p_tp += 4u * ROWB;
-            p_tm += 4u * ROWB;
-            if (NDIM >= 4) {
-                p_u2 += 4u * ROWB;
-                p_d2 += 4u * ROWB;
-            }
-            p_dst += 4u * ROWB;
-            asm volatile("" : "+l"(p_tp), "+l"(p_tm), "+l"(p_u2), "+l"(p_d2), "+l"(p_dst));
-            s_c += 4u * ROWB;
-            s_left += 4u * ROWB;
-            s_right += 4u * ROWB;
+            p_dst += PASSB;
         }
 
         // ---- the omega work-item's draw (gid = V) and the step's final seed -------------------------------------
@@ -853,43 +864,43 @@ __global__ void __launch_bounds__(288, 3) lattice_ptile_kernel(const LatticeArgs
             if (lcg_event(sv & LCG_MASK, t1, t2)) atomicMin((unsigned long long *)A.event_key, event_key(A.step_index, chain, Vg));
             A.seed_out[chain] = lcg_next_seed(t2);
         }
-        // ---- the warp's share of the tile's observable partial; the warp leaves the stage ---------------------------
+        // ---- the warp's share of the tile's observable partial ---------------------------------------------------------
         if (A.partials) {
             float a1l, a1h, a2l, a2h;
             upk(ACC1, a1l, a1h);
             upk(ACC2, a2l, a2h);
             const double a1 = warp_sum((double)a1l + (double)a1h), a2 = warp_sum((double)a2l + (double)a2h);
-            if (lane == 0) { S.red[st][0][warp] = a1; S.red[st][1][warp] = a2; }
+            if (lane == 0) { S.red[hs][0][warp] = a1; S.red[hs][1][warp] = a2; }
         }
-        __syncwarp();
-        if (lane == 0) tile_mbar_arrive(smem0 + 16u + 8u * st);
     }
     if (nclamp) atomicAdd(A.nclamped, (unsigned long long)nclamp);
 }
 
-// SQ_PTILE=0 in the environment: the one-tile-per-CTA kernel (A/B knob); default: the persistent two-stage kernel
-static bool ptile_on() {
+// SQ_PTILE=0 in the environment: the one-tile-per-CTA kernel (A/B knob); default: the row-block streaming kernel
+static bool rows_on() {
     static const bool on = !(getenv("SQ_PTILE") && atoi(getenv("SQ_PTILE")) == 0);
     return on;
 }
-// bytes of one staged tile: [halo | rows | halo] per run of rows inside a plane
-static size_t tile_stage_bytes(int L0, int L1, int tpr_log, int R) {
-    const unsigned rows_per_cta = (256u >> tpr_log) * (unsigned)R;
+// shared memory a CTA needs.  One-tile kernel: a line for the mbarrier + the tile as [halo | rows | halo] per run of rows
+// inside a plane.  Row-block kernel: the barrier line + three stages of (5 RPP + 2) rows (3 RPP + 2 in three dimensions).
+size_t tile_smem_bytes(int ndim, int L0, int L1, int tpr_log, int R) {
+    const unsigned rpp = 256u >> tpr_log, rows_per_cta = rpp * (unsigned)R;
+    if (rows_on()) {
+        const size_t stage = ((size_t)((ndim >= 4 ? 5u : 3u) * rpp + 2u) * (size_t)L0 * 4u + 127) / 128 * 128;
+        return 128 + ROWS_D * stage;
+    }
     const unsigned seg_rows = rows_per_cta < (unsigned)L1 ? rows_per_cta : (unsigned)L1, nseg = rows_per_cta / seg_rows;
-    return (size_t)nseg * (seg_rows + 2u) * (size_t)L0 * 4u;
+    return 128 + (size_t)nseg * (seg_rows + 2u) * (size_t)L0 * 4u;
 }
-// shared memory a CTA needs: one line of mbarriers + its stage(s)
-size_t tile_smem_bytes(int L0, int L1, int tpr_log, int R) {
-    const size_t stage = tile_stage_bytes(L0, L1, tpr_log, R);
-    return ptile_on() ? 128 + 2 * ((stage + 127) / 128 * 128) : 128 + stage;
-}
-// the tile must be a whole number of planes or divide one (runs of rows never straddle a plane edge); tpr_log = log2 of the
-// threads per row (row length / sites per strip).  Three CTAs per SM: 72 KB each.
-bool tile_shape_ok(int L0, int L1, int tpr_log, int R) {
-    const unsigned rows_per_cta = (256u >> tpr_log) * (unsigned)R;
+// the tile must be a whole number of planes or divide one (the marching kernel's rows of a thread never straddle a plane
+// edge); tpr_log = log2 of the threads per row (row length / 4).  Row-block kernel: a pass (1024 / L0 rows) must divide a
+// plane.  Three CTAs per SM: 72 KB each.
+bool tile_shape_ok(int ndim, int L0, int L1, int tpr_log, int R) {
+    const unsigned rpp = 256u >> tpr_log, rows_per_cta = rpp * (unsigned)R;
     if (L1 % R != 0 || R % 4 != 0) return false;
     if (!(rows_per_cta % (unsigned)L1 == 0 || (unsigned)L1 % rows_per_cta == 0)) return false;
-    return tile_smem_bytes(L0, L1, tpr_log, R) <= 72 * 1024;
+    if (rows_on() && (unsigned)L1 % rpp != 0) return false;
+    return tile_smem_bytes(ndim, L0, L1, tpr_log, R) <= 72 * 1024;
 }
 
 // Instantiated: 4-site strips, event-free steps.  (8-site strips -- 124 registers, two CTAs per SM -- were measured at
@@ -897,22 +908,21 @@ bool tile_shape_ok(int L0, int L1, int tpr_log, int R) {
 // which shares this kernel's tiles and jump tables.)
 template <int MATH, int NDIM, int POT, int L0T>
 static cudaError_t tile_go(const LatticeArgs &A, dim3 grid, size_t smem, cudaStream_t st) {
-    if (ptile_on()) {
+    if (rows_on()) {
         int dev = 0, sms = 0, per_sm = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        auto kern = lattice_ptile_kernel<MATH, NDIM, POT, L0T>;
+        auto kern = lattice_rows_kernel<MATH, NDIM, POT, L0T>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 288, smem)) != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         const unsigned long long nt64 = (unsigned long long)grid.x * grid.y * grid.z;
-        if (nt64 >= (1ull << 31) || !A.tile_ctr) return cudaErrorInvalidValue;
+        if (nt64 >= (1ull << 31) || !A.tile_ctr || !A.rows_thr || A.m_R < 4) return cudaErrorInvalidValue;
         const unsigned ntiles = (unsigned)nt64, slots = (unsigned)(sms * per_sm);
-        static const unsigned pf = getenv("SQ_PTILE_PF") ? (unsigned)atoi(getenv("SQ_PTILE_PF")) : 7u;  // tuning knob: L2 prefetch mask
-        unsigned nb = ntiles < slots ? ntiles : slots;
-        if (getenv("SQ_DEBUG")) fprintf(stderr, "ptile: sms %d per_sm %d ntiles %u grid %u smem %zu\n", sms, per_sm, ntiles, nb, smem);
-        kern<<<nb, 288, smem, st>>>(A, ntiles, grid.x, (unsigned)((smem - 128) / 2), pf);
+        const unsigned nb = ntiles < slots ? ntiles : slots;
+        if (getenv("SQ_DEBUG")) fprintf(stderr, "rows: sms %d per_sm %d ntiles %u grid %u smem %zu\n", sms, per_sm, ntiles, nb, smem);
+        kern<<<nb, 288, smem, st>>>(A, ntiles, grid.x, (unsigned)((smem - 128) / ROWS_D));
         return cudaGetLastError();
     }
     if (smem > 48 * 1024) {  // (idempotent; the attribute is per function)
@@ -938,7 +948,7 @@ static cudaError_t tile_pot(const LatticeArgs &A, dim3 grid, size_t smem, cudaSt
 
 cudaError_t launch_lattice_tile(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream) {
     dim3 grid((unsigned)ctas_per_slice, (unsigned)A.nt, (unsigned)A.nchains);
-    const size_t smem = tile_smem_bytes((int)A.dim[0], (int)A.dim[1], A.m_tpr_log, A.m_R);
+    const size_t smem = tile_smem_bytes(A.ndim, (int)A.dim[0], (int)A.dim[1], A.m_tpr_log, A.m_R);
     if (A.m_w != 4 || A.n_rebase != 0) return cudaErrorInvalidValue;
     if (A.ndim == 3) return math ? tile_pot<1, 3>(A, grid, smem, stream) : tile_pot<0, 3>(A, grid, smem, stream);
     if (A.ndim == 4) return math ? tile_pot<1, 4>(A, grid, smem, stream) : tile_pot<0, 4>(A, grid, smem, stream);
