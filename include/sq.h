@@ -88,6 +88,7 @@ typedef struct sq_params {
 #define SQ_FLAG_NO_OBSERVABLES 1 /* LATTICE: skip the per-step reductions          */
 #define SQ_FLAG_FORCE_STREAMING 2 /* LATTICE: never use the on-chip resident kernel */
 #define SQ_FLAG_GENERIC_KERNEL 4  /* LATTICE: never use the row-marching fp32 kernel    */
+#define SQ_FLAG_ROWBLOCK_KERNEL 8 /* LATTICE d>=3 fp32: the row-block staging kernel instead of the tile kernel */
 
 /* What sq_measure copies out.  Pointer members are caller-allocated (or NULL to
  * skip).  Replaces the per-frame blocking reads tauhost.c:504-515. */

@@ -9,6 +9,7 @@ works anywhere, but creating a context without the CUDA library or a GPU raises.
 from .lib import (  # noqa: F401
     SQ_KERNEL_COMPAT1D, SQ_KERNEL_LATTICE, SQ_REAL_F32, SQ_REAL_F64, SQ_MATH_ACCURATE,
     SQ_MATH_FAST, SQ_POT_HARMONIC, SQ_POT_DOUBLEWELL, SQ_POT_PHI4, SQ_FLAG_NO_OBSERVABLES,
+    SQ_FLAG_FORCE_STREAMING, SQ_FLAG_GENERIC_KERNEL, SQ_FLAG_ROWBLOCK_KERNEL,
     SqError, SqParams, SqObs, SqRngEntry, SqFrameRec, SQ_FRAMES_MAX, Context, Session, rng_resolve, load, library_path, build,
     exported_symbols,
 )

@@ -205,6 +205,8 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
         const int64_t L0 = p.dims[0], L1 = p.dims[1], nrows = c->vslice / L0;
         static const int force_R = getenv("SQ_MARCH_R") ? atoi(getenv("SQ_MARCH_R")) : 0;    // tuning knob
         static const int tile_w = getenv("SQ_TILE") ? (atoi(getenv("SQ_TILE")) ? 4 : 0) : SQ_TILE_DEFAULT;  // 0: marching kernel only, 4: tile kernel
+        static const bool env_rows = getenv("SQ_ROWS") && atoi(getenv("SQ_ROWS")) == 1;   // A/B knob
+        const bool want_rows = env_rows || (p.flags & SQ_FLAG_ROWBLOCK_KERNEL);
         int best = 0, best_w = 4;
         for (int attempt = 0; attempt < 3 && !best; ++attempt) {
             // attempt 0: tile kernel with the requested strip width; 1: tile kernel with 4-site strips; 2: marching kernel
@@ -219,7 +221,7 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
             while ((1 << tlog) < tpr) tlog++;
             for (int R = force_R ? force_R : 16; R >= 1; R >>= 1) {
                 if (L1 % R != 0 || nrows % (rg * R) != 0 || nrows / (rg * R) > 65535) continue;
-                if (tile && !tile_shape_ok(p.ndim, (int)L0, (int)L1, tlog, R)) continue;
+                if (tile && !tile_shape_ok(p.ndim, (int)L0, (int)L1, tlog, R, want_rows)) continue;
                 const int64_t ctas = nrows / (rg * R) * c->nt * p.nchains;
                 best = R;  // the largest that fits, unless a smaller one is needed to fill the GPU
                 best_w = w;
@@ -228,6 +230,7 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
             if (best) {
                 c->march_ok = true;
                 c->tile_ok = tile;
+                c->rows_ok = tile && want_rows;
                 c->m_R = best;
                 c->m_w = best_w;
                 c->m_tpr_log = tlog;
@@ -503,7 +506,7 @@ LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */
     A.stride_jump = jump_entry((u64)A.strips_per_cta_iter * (u64)vec);
     A.vol_jump = jump_entry((u64)c->V);
     A.jump = c->d_jump;
-    A.m_on = c->march_ok ? (c->tile_ok ? 2 : 1) : 0;
+    A.m_on = c->march_ok ? (c->tile_ok ? (c->rows_ok ? 3 : 2) : 1) : 0;
     A.t_dck = LCG_BETA * (u64)p.dims[0] * jump_entry((u64)p.dims[0]).g0;
     A.m_w = c->m_w;
     A.t_dc1 = (u64)(p.dims[0] - (c->m_w - 1)) * LCG_A;   // from a strip's last site to the next row's first
@@ -529,7 +532,7 @@ LatticeArgs sq_lattice_args(sq_ctx *c, double dtau, int k /* step in sequence */
 }
 
 int sq_launch_update(sq_ctx *c, const LatticeArgs &A) {
-    if (A.m_on == 2 && A.n_rebase == 0) CK(launch_lattice_tile(A, c->p.math, c->ctas_per_slice, c->stream));  // (entries: marching kernel)
+    if (A.m_on >= 2 && A.n_rebase == 0) CK(launch_lattice_tile(A, c->p.math, c->ctas_per_slice, c->stream));  // (entries: marching kernel)
     else if (A.m_on) CK(launch_lattice_march(A, c->p.math, c->ctas_per_slice, c->stream));
     else CK(launch_lattice_step(A, c->p.real, c->p.math, c->ctas_per_slice, c->stream));
     return SQ_OK;

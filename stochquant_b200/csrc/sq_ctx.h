@@ -78,6 +78,7 @@ struct sq_ctx {
     bool per_chain_coupling = false;
     // row-marching kernel (sq_march.cu): geometry + jump tables, when the shape qualifies
     bool march_ok = false;
+    bool rows_ok = false;   // ... through the row-block staging kernel (SQ_FLAG_ROWBLOCK_KERNEL / SQ_ROWS=1): lattice_rows_kernel
     bool tile_ok = false;   // ... and its tiles can be staged in shared memory: lattice_tile_kernel (sq_tile.cu)
     int m_R = 0, m_tpr_log = 0, m_w = 4;
     JumpEntry *l_cta_jump = nullptr, *l_thr_jump = nullptr;

@@ -121,7 +121,7 @@ struct LatticeArgs {
     double *partials;    // [nchains][nt][ctas_per_slice][2] (sum phi, sum phi^2), or null
     unsigned long long *nclamped;
     // ---- row-marching kernel (sq_march.cu), fp32 d = 3,4 with dims[0]/4 a power of two <= 256 ----
-    int m_on;                    // 1: launch lattice_march_kernel (gridDim.x = its own CTAs per slice), 2: lattice_tile_kernel
+    int m_on;                    // 1: launch lattice_march_kernel (gridDim.x = its own CTAs per slice), 2: lattice_tile_kernel, 3: lattice_rows_kernel
     int m_R;                     // consecutive rows (x1) per thread; divides dims[1]
     int m_w;                     // sites per strip: 4 (marching kernel, tile kernel) or 8 (tile kernel)
     int m_tpr_log;               // log2(threads per row) = log2(dims[0] / m_w)
@@ -151,8 +151,8 @@ cudaError_t preload_lattice_step(int real, int math, int ndim);
 cudaError_t launch_lattice_march(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream);
 // sq_tile.cu: the same tiles staged through shared memory by bulk asynchronous copies (LatticeArgs::m_on == 2)
 cudaError_t launch_lattice_tile(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream);
-bool tile_shape_ok(int ndim, int L0, int L1, int tpr_log, int R);
-size_t tile_smem_bytes(int ndim, int L0, int L1, int tpr_log, int R);
+bool tile_shape_ok(int ndim, int L0, int L1, int tpr_log, int R, bool rows);
+size_t tile_smem_bytes(int ndim, int L0, int L1, int tpr_log, int R, bool rows);
 
 struct FinalizeArgs {
     int nt, nchains, ctas_per_slice;

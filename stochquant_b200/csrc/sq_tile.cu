@@ -472,16 +472,40 @@ __global__ void __launch_bounds__(256, NP == 4 ? 2 : TILE_MINB) lattice_tile_ker
 //     instead of 2.6, ncu);
 //   - the producer role rotating over the eight computing warps instead of a ninth warp: 219;
 //   - whole tiles in two stages, claimed dynamically, t+-1 / x2+-1 still direct loads: 347 -- hiding the CTA start-up
-//     buys nothing while the direct loads bound the passes.
-constexpr unsigned ROWS_D = 3;  // stages
+//     buys nothing while the direct loads bound the passes;
+//   - this kernel + cp.async.bulk.prefetch.L2 of the slice above / plane above 2..8 passes ahead of their copies: 308
+//     against 355 without.
+#ifndef ROWS_STAGES
+#define ROWS_STAGES 2
+#endif
+constexpr unsigned ROWS_D = ROWS_STAGES;  // stages (the computing warps' pass loop is unrolled by it: a stage's address is an immediate)
+#ifndef ROWS_WAIT_NS
+#define ROWS_WAIT_NS 0      // > 0: waits park the warp for up to this many ns per try (suspend-time hint)
+#endif
+#if ROWS_WAIT_NS > 0
+#define ROWS_WAIT(bar, par) tile_mbar_wait_hint((bar), (par), ROWS_WAIT_NS)
+#else
+#define ROWS_WAIT(bar, par) tile_mbar_wait((bar), (par))
+#endif
+#ifndef ROWS_ARRIVE_ALL
+#define ROWS_ARRIVE_ALL 0   // 1: every lane arrives on empty[s] (count 256, no __syncwarp) ; 0: lane 0 of each warp (count 8)
+#endif
 struct RowsShared {
-    TileHdr H[2];          // by tile parity
-    double red[2][2][8];
-    int chain[2];
-    int end[2];            // no tile: the grid has run out of them
+    TileHdr H[3];          // by tile number mod 3 (the producer writes tile t+1's while t is computed and t-1 retired)
+    double red[2][2][8];   // by tile parity
+    int chain[3];
+    int end[3];            // no tile: the grid has run out of them
     int skip;
 };
 
+// wait that parks the warp in hardware for up to `ns` per try instead of spinning through the issue slots
+__device__ __forceinline__ void tile_mbar_wait_hint(unsigned bar, unsigned parity, unsigned ns) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@!p bra W_%=;\n\t}" ::"r"(bar), "r"(parity), "r"(ns) : "memory");
+}
 __device__ __forceinline__ void tile_mbar_arrive(unsigned bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
 }
@@ -508,7 +532,7 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
         S.skip = *((volatile const u64 *)A.event_key) != NO_EVENT;
         for (unsigned s = 0; s < ROWS_D; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem0 + 8u * s) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" ::"r"(smem0 + 32u + 8u * s) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem0 + 32u + 8u * s), "r"(ROWS_ARRIVE_ALL ? 256u : 8u) : "memory");
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -591,13 +615,13 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
             return true;
         };
         // ---- everybody has left the tile in header slot hs: its observable partial, and a slab ring's flag (lane 0) ----
-        auto retire = [&](const unsigned hs) {
+        auto retire = [&](const unsigned hs, const unsigned rs) {
             if (lane == 0) {
                 const TileHdr &H = S.H[hs];
                 const int tl = H.tl, chain = S.chain[hs];
                 if (A.partials) {
                     double s1 = 0, s2 = 0;
-                    for (int q = 0; q < 8; ++q) { s1 += S.red[hs][0][q]; s2 += S.red[hs][1][q]; }
+                    for (int q = 0; q < 8; ++q) { s1 += S.red[rs][0][q]; s2 += S.red[rs][1][q]; }
                     double *p = A.partials + (((long long)chain * A.nt + tl) * cps + H.bx) * 2;
                     p[0] = s1;
                     p[1] = s2;
@@ -621,6 +645,7 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
         };
         const unsigned stage_bytes = (NSTREAM * RPP + 2u) * ROWB;
         unsigned stage = 0, phase = 0, g = 0, t = 0;  // stage / phase of pass g ; t: tiles started
+        unsigned hs = 0;                              // header slot of tile t (t mod 3)
         bool more = claim(0);
         if (!more && lane == 0) {
             S.end[0] = 1;
@@ -628,7 +653,8 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
         }
 #pragma unroll 1
         while (more) {
-            const TileHdr &H = S.H[t & 1u];
+            const TileHdr &H = S.H[hs];
+            const unsigned hs_next = hs == 2 ? 0u : hs + 1u, hs_prev = hs == 0 ? 2u : hs - 1u;
             // lane roles: 0 rows, 1 row before, 2 row after, 3 slice above, 4 slice below, 5 plane above, 6 plane below
             const char *base = (lane == 3) ? H.tp : (lane == 4 ? H.tm : H.cur);
             const unsigned row0 = H.bx * (RPP * R);
@@ -636,12 +662,13 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
             const unsigned dst_row = lane == 0 ? 1u : (lane == 1 ? 0u : (lane == 2 ? RPP + 1u : (lane - 2u) * RPP + 2u));
             const unsigned bytes = (lane == 1 || lane == 2) ? ROWB : PASSB;
             const bool active = lane < NSTREAM + 2u;
+            bool next = false;
 #pragma unroll 1
             for (unsigned p = 0; p < R; ++p) {
                 if (g >= ROWS_D) {
-                    tile_mbar_wait(smem0 + 32u + 8u * stage, phase ^ 1u);  // everybody has left pass g - D
+                    ROWS_WAIT(smem0 + 32u + 8u * stage, phase ^ 1u);  // everybody has left pass g - D
                     // ... if that was the first pass of this tile, every warp has written its share of the tile before's partial
-                    if (p == ROWS_D && t >= 1) retire((t - 1u) & 1u);
+                    if (p == ROWS_D && t >= 1) retire(hs_prev, (t - 1u) & 1u);
                 }
                 long long off = 0;  // rows, relative to the block's first row
                 if (lane == 1) off = (x1a == 0) ? (long long)L1 - 1 : -1;
@@ -664,20 +691,24 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
                     stage = 0;
                     phase ^= 1u;
                 }
+                // the NEXT tile is claimed and its header worked out while this one streams (the counter's round trip and the
+                // header arithmetic would otherwise stall the stages at every tile edge: 9 % of the stall samples)
+                if (p == 0) next = claim(hs_next);
             }
             ++t;
-            more = claim(t & 1u);
+            hs = hs_next;
+            more = next;
             if (!more) {  // tell the computing warps: the next pass's stage carries `end` instead of data
                 if (g >= ROWS_D) tile_mbar_wait(smem0 + 32u + 8u * stage, phase ^ 1u);
                 if (lane == 0) {
-                    S.end[t & 1u] = 1;
+                    S.end[hs] = 1;
                     tile_mbar_arrive(smem0 + 8u * stage);
                 }
             }
         }
         if (t >= 1) {  // the last tile's partial and flag: the computing warps arrive once more when they see `end`
             tile_mbar_wait(smem0 + 32u + 8u * stage, phase);
-            retire((t - 1u) & 1u);
+            retire(hs == 0 ? 2u : hs - 1u, (t - 1u) & 1u);
         }
         // the last CTA out rearms the counters for the next launch on the stream
         if (lane == 0 && atomicAdd(A.tile_ctr + 1, 1u) == gridDim.x - 1) {
@@ -702,15 +733,21 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
     const unsigned thr_off = E.thr_off;                       // ty L0 + 4 tx
     const unsigned o_c = 128u + E.s_c, o_left = 128u + E.s_left, o_right = 128u + E.s_right;  // byte offsets inside a stage (+ the barrier line)
     const u64 e_a = E.a, e_g0 = E.g0, e_bg1 = E.bg1, e_ck = E.ck_off;
-    unsigned stage = 0, phase = 0;
+    unsigned phase = 0, hs = 0;  // (R is a multiple of the stage count: every tile starts in stage 0)
+    auto leave = [&](const unsigned st) {  // the thread / warp has read what it needs from stage st
+        if (ROWS_ARRIVE_ALL) {
+            tile_mbar_arrive(smem0 + 32u + 8u * st);
+        } else {
+            __syncwarp();
+            if (lane == 0) tile_mbar_arrive(smem0 + 32u + 8u * st);
+        }
+    };
 
 #pragma unroll 1
     for (unsigned t = 0;; ++t) {
-        const unsigned hs = t & 1u;
-        tile_mbar_wait(smem0 + 8u * stage, phase);  // the tile's first stage: header written (and the rows landed)
+        ROWS_WAIT(smem0, phase);  // the tile's first stage: header written (and the rows landed)
         if (S.end[hs]) {  // (one more arrival: the producer then knows the last tile's partial is complete)
-            __syncwarp();
-            if (lane == 0) tile_mbar_arrive(smem0 + 32u + 8u * stage);
+            leave(0);
             break;
         }
         const TileHdr &H = S.H[hs];
@@ -734,8 +771,7 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
         (void)K_lam; (void)K_m2;
         pair_t ACC1 = 0, ACC2 = 0;
 
-#pragma unroll 1
-        for (unsigned p = 0; p < R; ++p) {
+        auto pass = [&](const unsigned p, const unsigned stage) {
             // ---- noise phase: W draws in t2 form, Box-Muller (no field data: runs ahead of the stage) ---------------
             const unsigned T0l = Tl, T0h = Th;
             unsigned tl_ = Tl, th_ = Th, um = 0xFFFFFFFFu;
@@ -779,7 +815,7 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
                 ck += A.p_dck;
             }
             // ---- stencil phase: everything from the stage ------------------------------------------------------------
-            tile_mbar_wait(smem0 + 8u * stage, phase);
+            ROWS_WAIT(smem0 + 8u * stage, phase);
             const unsigned sb = smem0 + stage * stage_stride;
             pair_t C[NP], U1[NP], D1[NP];
             ulonglong2 U2, D2, TP, TM;
@@ -824,13 +860,7 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
                 ACC1 = add2(ACC1, C[q]);           // observables of the pre-update field
                 ACC2 = fma2(C[q], C[q], ACC2);
             }
-            // the warp has read what it needs from the stage
-            __syncwarp();
-            if (lane == 0) tile_mbar_arrive(smem0 + 32u + 8u * stage);
-            if (++stage == ROWS_D) {
-                stage = 0;
-                phase ^= 1u;
-            }
+            leave(stage);
             // clamp (tau_kernel.cl:122-132) and RNG events: one test per strip for both rare cases
             if (__builtin_expect(!(amax < 1000.0f) | (um < 32768u), 0)) {
                 bool replayed = false;  // an event in this strip: the launch is redone, its clamp hits are not counted
@@ -853,6 +883,12 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
                 if (push_hi) *reinterpret_cast<ulonglong2 *>((char *)A.push_ghost[1] + oo) = make_ulonglong2(V[0], V[1]);
             }
             p_dst += PASSB;
+        };
+#pragma unroll 1
+        for (unsigned p = 0; p < R; p += ROWS_D) {
+#pragma unroll
+            for (unsigned u = 0; u < ROWS_D; ++u) pass(p + u, u);
+            phase ^= 1u;
         }
 
         // ---- the omega work-item's draw (gid = V) and the step's final seed -------------------------------------
@@ -870,37 +906,33 @@ __global__ void __launch_bounds__(288, 3) lattice_rows_kernel(const LatticeArgs 
             upk(ACC1, a1l, a1h);
             upk(ACC2, a2l, a2h);
             const double a1 = warp_sum((double)a1l + (double)a1h), a2 = warp_sum((double)a2l + (double)a2h);
-            if (lane == 0) { S.red[hs][0][warp] = a1; S.red[hs][1][warp] = a2; }
+            if (lane == 0) { S.red[t & 1u][0][warp] = a1; S.red[t & 1u][1][warp] = a2; }
         }
+        hs = hs == 2 ? 0u : hs + 1u;
     }
     if (nclamp) atomicAdd(A.nclamped, (unsigned long long)nclamp);
 }
 
-// SQ_PTILE=0 in the environment: the one-tile-per-CTA kernel (A/B knob); default: the row-block streaming kernel
-static bool rows_on() {
-    static const bool on = !(getenv("SQ_PTILE") && atoi(getenv("SQ_PTILE")) == 0);
-    return on;
-}
-// shared memory a CTA needs.  One-tile kernel: a line for the mbarrier + the tile as [halo | rows | halo] per run of rows
-// inside a plane.  Row-block kernel: the barrier line + three stages of (5 RPP + 2) rows (3 RPP + 2 in three dimensions).
-size_t tile_smem_bytes(int ndim, int L0, int L1, int tpr_log, int R) {
+// shared memory a CTA needs.  Tile kernel: a line for the mbarrier + the tile as [halo | rows | halo] per run of rows
+// inside a plane.  Row-block kernel: the barrier line + its stages of (5 RPP + 2) rows (3 RPP + 2 in three dimensions).
+size_t tile_smem_bytes(int ndim, int L0, int L1, int tpr_log, int R, bool rows) {
     const unsigned rpp = 256u >> tpr_log, rows_per_cta = rpp * (unsigned)R;
-    if (rows_on()) {
+    if (rows) {
         const size_t stage = ((size_t)((ndim >= 4 ? 5u : 3u) * rpp + 2u) * (size_t)L0 * 4u + 127) / 128 * 128;
         return 128 + ROWS_D * stage;
     }
     const unsigned seg_rows = rows_per_cta < (unsigned)L1 ? rows_per_cta : (unsigned)L1, nseg = rows_per_cta / seg_rows;
     return 128 + (size_t)nseg * (seg_rows + 2u) * (size_t)L0 * 4u;
 }
-// the tile must be a whole number of planes or divide one (the marching kernel's rows of a thread never straddle a plane
-// edge); tpr_log = log2 of the threads per row (row length / 4).  Row-block kernel: a pass (1024 / L0 rows) must divide a
-// plane.  Three CTAs per SM: 72 KB each.
-bool tile_shape_ok(int ndim, int L0, int L1, int tpr_log, int R) {
+// the tile must be a whole number of planes or divide one (the rows of a thread never straddle a plane edge); tpr_log = log2
+// of the threads per row (row length / 4).  Row-block kernel: a pass (1024 / L0 rows) must divide a plane, and the passes of a
+// tile a multiple of the stage count.  Three CTAs per SM: 72 KB each.
+bool tile_shape_ok(int ndim, int L0, int L1, int tpr_log, int R, bool rows) {
     const unsigned rpp = 256u >> tpr_log, rows_per_cta = rpp * (unsigned)R;
     if (L1 % R != 0 || R % 4 != 0) return false;
     if (!(rows_per_cta % (unsigned)L1 == 0 || (unsigned)L1 % rows_per_cta == 0)) return false;
-    if (rows_on() && (unsigned)L1 % rpp != 0) return false;
-    return tile_smem_bytes(ndim, L0, L1, tpr_log, R) <= 72 * 1024;
+    if (rows && ((unsigned)L1 % rpp != 0 || R % (int)ROWS_D != 0)) return false;
+    return tile_smem_bytes(ndim, L0, L1, tpr_log, R, rows) <= 72 * 1024;
 }
 
 // Instantiated: 4-site strips, event-free steps.  (8-site strips -- 124 registers, two CTAs per SM -- were measured at
@@ -908,7 +940,7 @@ bool tile_shape_ok(int ndim, int L0, int L1, int tpr_log, int R) {
 // which shares this kernel's tiles and jump tables.)
 template <int MATH, int NDIM, int POT, int L0T>
 static cudaError_t tile_go(const LatticeArgs &A, dim3 grid, size_t smem, cudaStream_t st) {
-    if (rows_on()) {
+    if (A.m_on == 3) {
         int dev = 0, sms = 0, per_sm = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
@@ -918,7 +950,7 @@ static cudaError_t tile_go(const LatticeArgs &A, dim3 grid, size_t smem, cudaStr
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 288, smem)) != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         const unsigned long long nt64 = (unsigned long long)grid.x * grid.y * grid.z;
-        if (nt64 >= (1ull << 31) || !A.tile_ctr || !A.rows_thr || A.m_R < 4) return cudaErrorInvalidValue;
+        if (nt64 >= (1ull << 31) || !A.tile_ctr || !A.rows_thr || A.m_R < 4 || A.m_R % (int)ROWS_D != 0) return cudaErrorInvalidValue;
         const unsigned ntiles = (unsigned)nt64, slots = (unsigned)(sms * per_sm);
         const unsigned nb = ntiles < slots ? ntiles : slots;
         if (getenv("SQ_DEBUG")) fprintf(stderr, "rows: sms %d per_sm %d ntiles %u grid %u smem %zu\n", sms, per_sm, ntiles, nb, smem);
@@ -948,7 +980,7 @@ static cudaError_t tile_pot(const LatticeArgs &A, dim3 grid, size_t smem, cudaSt
 
 cudaError_t launch_lattice_tile(const LatticeArgs &A, int math, int ctas_per_slice, cudaStream_t stream) {
     dim3 grid((unsigned)ctas_per_slice, (unsigned)A.nt, (unsigned)A.nchains);
-    const size_t smem = tile_smem_bytes(A.ndim, (int)A.dim[0], (int)A.dim[1], A.m_tpr_log, A.m_R);
+    const size_t smem = tile_smem_bytes(A.ndim, (int)A.dim[0], (int)A.dim[1], A.m_tpr_log, A.m_R, A.m_on == 3);
     if (A.m_w != 4 || A.n_rebase != 0) return cudaErrorInvalidValue;
     if (A.ndim == 3) return math ? tile_pot<1, 3>(A, grid, smem, stream) : tile_pot<0, 3>(A, grid, smem, stream);
     if (A.ndim == 4) return math ? tile_pot<1, 4>(A, grid, smem, stream) : tile_pot<0, 4>(A, grid, smem, stream);

@@ -18,6 +18,7 @@ SQ_POT_HARMONIC, SQ_POT_DOUBLEWELL, SQ_POT_PHI4 = 0, 3, 4
 SQ_FLAG_NO_OBSERVABLES = 1
 SQ_FLAG_FORCE_STREAMING = 2
 SQ_FLAG_GENERIC_KERNEL = 4
+SQ_FLAG_ROWBLOCK_KERNEL = 8
 
 
 class SqError(RuntimeError):

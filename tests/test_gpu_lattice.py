@@ -462,3 +462,36 @@ def test_fast_math_is_one_definition_across_kernels(gpu_sq, oracle, dims, flag):
         assert np.array_equal(a.download(), b.download())
         a.close()
         b.close()
+
+
+@pytest.mark.parametrize("dims,pot", [((32, 32, 8, 6), 0), ((64, 16, 16, 4), 4), ((64, 32, 8), 4), ((256, 16, 8, 4), 0), ((32, 32, 4, 4), 4)])
+def test_rowblock_kernel_is_the_tile_kernel_bit_for_bit(gpu_sq, oracle, dims, pot):
+    """SQ_FLAG_ROWBLOCK_KERNEL (sq_tile.cu: lattice_rows_kernel -- every stencil operand staged per pass through shared
+    memory by a producer warp, tiles claimed from a counter) against the default tile kernel: same integer stream and the
+    same field bit for bit, also across an RNG event (the replayed step runs on the marching kernel in both), with several
+    chains (tiles of different chains share CTAs) and with the clamp firing.  The observables agree to fp32 summation
+    order only: a thread's partial sum runs over a different set of rows in the two kernels."""
+    V = int(np.prod(dims))
+    rng = np.random.default_rng(32)
+    for seed, nch, c in ((1242608872, 3, 1.0), (seed_with_retry_at(oracle, V // 2 + 3), 1, 1.0), (99, 2, 600.0)):
+        phi0 = (rng.normal(size=V * nch) * 0.5).astype(np.float32)
+        kw = dict(real="f32", math="fast", potential=pot, m2=0.25, lam=0.5, seed=seed, nchains=nch, noise_c=c)
+        a = gpu_sq.Context(dims, **kw)
+        b = gpu_sq.Context(dims, flags=gpu_sq.SQ_FLAG_ROWBLOCK_KERNEL, **kw)
+        for k in range(nch):
+            a.upload(phi0[k * V:(k + 1) * V], chain=k)
+            b.upload(phi0[k * V:(k + 1) * V], chain=k)
+        for _ in range(2):
+            a.step(0.9 if c > 1 else DTAU, 7)
+            b.step(0.9 if c > 1 else DTAU, 7)
+        ma, mb = a.measure(), b.measure()
+        assert ma["seed"] == mb["seed"] and ma["nclamped"] == mb["nclamped"]
+        if c > 1:
+            assert ma["nclamped"] > 0
+        for k in ("slice_x", "slice_xx0", "mean_phi", "mean_phi2"):
+            x, y = np.asarray(ma[k], dtype=np.float64), np.asarray(mb[k], dtype=np.float64)
+            assert np.allclose(x, y, rtol=2e-5, atol=2e-5 * max(1.0, float(np.abs(x).max()))), (k, np.abs(x - y).max())
+        for k in range(nch):
+            assert np.array_equal(a.download(chain=k), b.download(chain=k))
+        a.close()
+        b.close()

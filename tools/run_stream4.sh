@@ -11,5 +11,5 @@ try:
 except Exception as e:
     print("bench $w failed", e); print(open("gpurun_out/${tag}_$w.err").read()[-1500:])
 PY
-grep ptile gpurun_out/${tag}_$w.err | head -1
+grep -E "ptile|rows:" gpurun_out/${tag}_$w.err | head -1
 done
