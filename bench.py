@@ -499,11 +499,13 @@ def ring_block(sq, np, torch, dist, timer, world, rank, local, args):
         torch.cuda.synchronize()
     for _ in range(warm):
         ctx.step(dtau, loops)
+    # (the counters are read OUTSIDE the barrier-bracketed region: reading them takes a rank-dependent while, and in a ring
+    # one late rank is waited for by all the others inside their first timed step)
+    nv0 = nvlink_bytes(local) if rank == 0 else None
     barrier()
-    nv0 = nvlink_bytes(local)
     ms = timer.frames(ctx, dtau, loops, steps, 0)
     barrier()
-    nv1 = nvlink_bytes(local)
+    nv1 = nvlink_bytes(local) if rank == 0 else None
     t = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
