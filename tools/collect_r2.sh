@@ -16,4 +16,6 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:rowr
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:lattice_tile --launch-skip 30 -c 1 -o $out/ncu_c3_tile -f python bench.py --workload c3 --steps 1 --warmup 3 --no-extras --no-e2e --no-cpu-baseline > $out/ncu_c3.log 2>&1; tail -1 $out/ncu_c3.log
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:lattice_tile --launch-skip 12 -c 1 -o $out/ncu_slab_tile -f python bench.py --workload slab --steps 1 --warmup 3 --no-extras --no-e2e --no-cpu-baseline > $out/ncu_slab.log 2>&1; tail -1 $out/ncu_slab.log
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:find_events --launch-skip 4 -c 1 -o $out/ncu_finder -f python bench.py --workload c4s --steps 1 --warmup 3 --no-extras > $out/ncu_finder.log 2>&1; tail -1 $out/ncu_finder.log
-ls -la $out | head -40
+SQ_ROWS=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:lattice_rows --launch-skip 12 -c 1 -o $out/ncu_slab_rows -f python bench.py --workload slab --steps 1 --warmup 3 --no-extras --no-e2e --no-cpu-baseline > $out/ncu_slab_rows.log 2>&1; tail -1 $out/ncu_slab_rows.log
+for w in c3 slab c5; do SQ_ROWS=1 timeout 300 python bench.py --workload $w --steps 10 --warmup 3 --no-extras --no-cpu-baseline > $out/bench_${w}_rowblock.json 2> $out/bench_${w}_rowblock.err; done
+ls -la $out | head -60
