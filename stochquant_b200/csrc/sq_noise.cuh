@@ -48,4 +48,12 @@ __device__ __forceinline__ float noise_fast(u64 t1, u64 t2) {
     return -__cosf(th) * rad;
 }
 
+// ACCURATE noise of one site, scaled and rounded to fp32, OUT OF LINE: the expression inlines to ~150 instructions (libdevice
+// cosf / logf with their slow paths); eight to sixteen copies per loop body pushed the fp32 lattice kernels past the
+// instruction cache (on-chip kernel: 84 -> 201 G site-updates/s when it became a call).  The streaming kernels keep it inline:
+// with their ~70 live registers around the call the out-of-line form was measured slower (64^4: 98 -> 108 us per step).
+static __device__ __noinline__ float noise_accurate_dw(unsigned u1, unsigned u2, double nscale) {
+    return (float)__dmul_rn(nscale, noise_accurate((u64)u1 << 16, (u64)u2 << 16));
+}
+
 }  // namespace sq

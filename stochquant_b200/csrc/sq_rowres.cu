@@ -109,12 +109,8 @@ __device__ __forceinline__ float4 lds_f4(unsigned a) {
     return v;
 }
 
-// ACCURATE noise out of line: eight inlined copies of logf / cosf / sqrtf and the fp64 products per role loop made the
-// kernel 12 k instructions (twice the FAST instance) -- no longer resident in the instruction caches (84 G site-updates/s
-// against 179 for the round-1 kernel); one shared copy restores it.
-__device__ __noinline__ float noise_accurate_dw(unsigned u1, unsigned u2, double nscale) {
-    return (float)__dmul_rn(nscale, noise_accurate((u64)u1 << 16, (u64)u2 << 16));
-}
+// (ACCURATE noise is the out-of-line noise_accurate_dw of sq_noise.cuh: eight inlined copies of logf / cosf / sqrtf and the
+// fp64 products per role loop made the kernel 12 k instructions -- no longer resident in the instruction caches.)
 
 // cold: exact event test of the w draws of a strip from its start seed (literal replay is the host's job)
 __device__ __noinline__ void stripw_events_cold(u64 *event_key_ptr, int step, u64 sm, u64 g0, int w) {

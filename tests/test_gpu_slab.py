@@ -113,6 +113,28 @@ def test_ring_equals_single_context(gpu_sq):
     assert maxabs(np.concatenate([r["slice_xx0"] for r in res]), m["slice_xx0"]) < 1e-12
 
 
+@pytest.mark.parametrize("dims,nranks", [((32, 32, 4, 12), 3), ((64, 16, 16, 8), 2), ((256, 8, 4, 8), 4)])
+def test_ring_rowblock_kernel_equals_single_context(gpu_sq, oracle, dims, nranks):
+    """The slab ring on the row-block staging kernel (SQ_FLAG_ROWBLOCK_KERNEL: the producer warp waits for the
+    neighbours' flags, raises them when a boundary slice's last tile retires; the computing warps push the
+    boundary slices): bit-identical to one context on the default tile kernel, with an RNG event on the way."""
+    V = int(np.prod(dims))
+    rng = np.random.default_rng(8)
+    phi0 = (rng.normal(size=V) * 0.5).astype(np.float32)
+    seed = seed_with_retry_at(oracle, V // 3 + 5)
+    whole = gpu_sq.Context(dims, real="f32", math="fast", potential=4, m2=0.25, lam=0.5, seed=seed)
+    whole.upload(phi0)
+    whole.step(DTAU, 5)
+    whole.step(DTAU, 6)
+    ref, seed_ref = whole.download(), whole.measure()["seed"]
+    whole.close()
+    res = ring_threads(gpu_sq, nranks, dims, phi0, [5, 6], real="f32", math="fast", pot=4, m2=0.25, lam=0.5, seed=seed,
+                       flags=gpu_sq.SQ_FLAG_ROWBLOCK_KERNEL)
+    assert all(r["seed"] == seed_ref for r in res)
+    assert np.array_equal(np.concatenate([r["field"] for r in res]), ref)
+    assert sum(r["nevents"] for r in res) >= nranks  # every rank replayed the event
+
+
 def test_multi_process_ring_over_ipc(gpu_sq, oracle, tmp_path):
     """One process per GPU (all GPUs of the box, up to 8), halo arenas mapped through CUDA IPC, NVLink
     peer stores: needs >= 2 GPUs."""
