@@ -495,3 +495,25 @@ def test_rowblock_kernel_is_the_tile_kernel_bit_for_bit(gpu_sq, oracle, dims, po
             assert np.array_equal(a.download(chain=k), b.download(chain=k))
         a.close()
         b.close()
+
+
+def test_chain_ensemble_with_jackknife_errors(gpu_sq):
+    """stochquant_b200.analysis over batched chains: <phi^2> of the 4-D free field from 24
+    independent chains in ONE context, error from a jackknife over chains of bin-averaged series, against the analytic
+    stationary value of the Euler-discretised process (see the test above)."""
+    from stochquant_b200 import analysis as an
+    L, eps, nch = 8, 0.05, 24
+    g = gpu_sq.Context((L, L, L, L), real="f32", math="fast", potential=0, nchains=nch)
+    g.step(eps, 300)
+    _, phi2 = an.collect_series(g, eps, 5, 60)        # [60 frames][24 chains]
+    g.close()
+    k = 2 * np.pi * np.arange(L) / L
+    s2 = 4 * np.sin(k / 2) ** 2
+    lam = s2[:, None, None, None] + s2[None, :, None, None] + s2[None, None, :, None] + s2[None, None, None, :] + 2.0
+    want = float(np.mean(1.0 / (lam * (1 - eps * lam / 2))))
+    per_chain = phi2.mean(axis=0)
+    val, err = an.jackknife(lambda a: a.mean(), per_chain)
+    assert abs(val - want) < 5 * err + 1e-3 * want, (val, want, err)
+    # chains are independent: the scatter over chains matches each chain's own binned error
+    _, e1 = an.binned_error(phi2[:, 0], 10)
+    assert 0.3 < e1 / per_chain.std(ddof=1) < 3.0
