@@ -745,6 +745,16 @@ u64 sq_host_seed_before(const sq_ctx *c, const std::vector<RebaseEntry> &entries
 //     appends a rebase entry and the sequence resumes at step k with the entry list;
 //   resident batch (one launch = many steps, output written at the end): nothing stands; the
 //     batch is re-run up to the event step, then ONE streaming step takes the event.
+// the on-chip path's deferred entry becomes the entry list of the streaming step that is enqueued next
+static int install_deferred(sq_ctx *c) {
+    if (c->deferred.empty()) return SQ_OK;
+    c->entries = c->deferred;
+    c->deferred.clear();
+    c->nevents += c->entries.size();
+    CK(cudaMemcpy(c->l_rebase, c->entries.data(), sizeof(RebaseEntry) * c->entries.size(), cudaMemcpyHostToDevice));
+    return SQ_OK;
+}
+
 static int sync_lattice(sq_ctx *c) {
     const int total = c->pend_total;
     int done = 0;
@@ -772,7 +782,12 @@ static int sync_lattice(sq_ctx *c) {
                 c->cur ^= 1;  // one launch, one buffer flip
                 done += n;
                 runs0 += n;
-                if (c->res_limit > 0) { c->res_limit = 0; c->force_stream = 1; }
+                if (c->res_limit > 0) {  // the re-run has reached the event step: it is a streaming step, entry in hand
+                    c->res_limit = 0;
+                    c->force_stream = 1;
+                    int ri = install_deferred(c);
+                    if (ri) return ri;
+                }
             } else {
                 // The launch stopped early (sq_resident.cu): keep everything up to the last checkpoint
                 // that EVERY CTA has written and that lies before the event, redo only the rest.
@@ -781,21 +796,45 @@ static int sync_lattice(sq_ctx *c) {
                 CK(cudaMemcpy(prog.data(), c->r_progress, sizeof(unsigned) * prog.size(), cudaMemcpyDeviceToHost));
                 const int reached = (int)*std::min_element(prog.begin(), prog.end());
                 const int c0 = std::min(reached, k) / RES_CKPT * RES_CKPT;
+                // The event's replay entry is resolved NOW: steps 0..k-1 of the launch are event-free as far as anyone has
+                // looked (the key is the minimum over everything detected), so the start seed of step k follows from the
+                // launch's by k whole-step advances, and the draw at the key's gid is replayed literally.  The streaming
+                // step that takes the event then runs WITH its entry instead of being launched once just to find the
+                // event again (one launch + one synchronisation less per event).  Should the re-run of c0..k-1 meet an
+                // EARLIER event (in rows a CTA had not reached when it left), this branch runs again and overwrites the
+                // entry; an earlier event inside step k itself is caught by the streaming step, which then drops it.
+                u64 S0;  // the launch's start seed
+                CK(cudaMemcpy(&S0, c->l_seeds[c->cur], sizeof(u64), cudaMemcpyDeviceToHost));
+                const JumpEntry vj = jump_entry((u64)c->V);
+                u64 S = S0, Sc0 = S0;
+                for (int i = 0; i < k; ++i) {  // what the kernel's omega thread does, step by step
+                    if (i == c0) Sc0 = S;
+                    u64 t1, t2;
+                    lcg_draw(lcg_apply(vj, S, 0) & LCG_MASK, (u64)c->V, t1, t2);
+                    S = lcg_next_seed(t2);
+                }
+                if (c0 == k) Sc0 = S;
+                {
+                    const u64 g = key & ((1ULL << KEY_CHAIN_SHIFT) - 1);
+                    const std::vector<RebaseEntry> none_yet;
+                    const HostDraw h = host_draw_literal(sq_host_seed_before(c, none_yet, 0, S, g), g);
+                    RebaseEntry e{};
+                    e.gid_start = g + 1;
+                    e.seed = h.seed_after;
+                    e.ov_gid = g;
+                    e.ov_t1 = h.t1;
+                    e.ov_t2 = h.t2;
+                    e.chain = 0;
+                    e.vseed = virtual_start_seed(e.seed, e.gid_start, c->h_jump.data());
+                    c->deferred.assign(1, e);
+                }
                 if (c0 > 0) {
                     const u64 none = NO_EVENT;
                     CK(cudaMemcpy(c->l_event, &none, sizeof(u64), cudaMemcpyHostToDevice));
                     key = NO_EVENT;  // (already cleared: skip the reset below)
                     CK(cudaMemcpyAsync(c->l_field[c->cur], c->r_ckpt + (size_t)((c0 / RES_CKPT) % RES_NCKPT) * (size_t)c->V,
                                        sizeof(float) * (size_t)c->V, cudaMemcpyDeviceToDevice, c->stream));
-                    u64 S;  // the step-start seed, c0 event-free steps on (what the kernel's omega thread does)
-                    CK(cudaMemcpy(&S, c->l_seeds[c->cur], sizeof(u64), cudaMemcpyDeviceToHost));
-                    const JumpEntry vj = jump_entry((u64)c->V);
-                    for (int i = 0; i < c0; ++i) {
-                        u64 t1, t2;
-                        lcg_draw(lcg_apply(vj, S, 0) & LCG_MASK, (u64)c->V, t1, t2);
-                        S = lcg_next_seed(t2);
-                    }
-                    CK(cudaMemcpy(c->l_seeds[c->cur], &S, sizeof(u64), cudaMemcpyHostToDevice));
+                    CK(cudaMemcpy(c->l_seeds[c->cur], &Sc0, sizeof(u64), cudaMemcpyHostToDevice));  // the seed c0 steps on
                     int rw = enqueue_resident_welford(c, c0, runs0);
                     if (rw) return rw;
                     done += c0;
@@ -806,7 +845,11 @@ static int sync_lattice(sq_ctx *c) {
                     c->launches++;
                 }
                 if (k > 0) c->res_limit = k;
-                else c->force_stream = 1;
+                else {
+                    c->force_stream = 1;
+                    int ri = install_deferred(c);
+                    if (ri) return ri;
+                }
             }
         } else {
             int ok = n;
@@ -824,6 +867,15 @@ static int sync_lattice(sq_ctx *c) {
                 const u64 g = key & ((1ULL << KEY_CHAIN_SHIFT) - 1);
                 u64 S;
                 CK(cudaMemcpy(&S, c->l_seeds[c->cur] + chain, sizeof(u64), cudaMemcpyDeviceToHost));
+                // (entries behind the new event were derived from a chain that this event changes: an entry installed ahead of
+                // its step by the on-chip path can be overtaken by an earlier event of the same step)
+                {
+                    const size_t before = c->entries.size();
+                    c->entries.erase(std::remove_if(c->entries.begin(), c->entries.end(),
+                                                    [&](const RebaseEntry &x) { return x.chain == chain && x.gid_start > g; }),
+                                     c->entries.end());
+                    c->nevents -= before - c->entries.size();  // (they never happened in the chain that stands)
+                }
                 const u64 sfull = sq_host_seed_before(c, c->entries, chain, S, g);
                 const HostDraw h = host_draw_literal(sfull, g);
                 RebaseEntry e{};
@@ -851,6 +903,7 @@ static int sync_lattice(sq_ctx *c) {
         if (rc) return rc;
     }
     c->entries.clear();
+    c->deferred.clear();
     c->force_stream = 0;
     c->res_limit = 0;
     c->runs = runs0;

@@ -103,6 +103,8 @@ struct sq_ctx {
     int pend_total = 0;   // steps the caller asked for
     int64_t pend_runs0 = 0;
     std::vector<RebaseEntry> entries;  // replay entries valid for the first step of the sequence
+    std::vector<RebaseEntry> deferred; // on-chip kernel: the entry of the event step, resolved when the launch was abandoned,
+                                       // installed when the re-run has reached that step
     // optional per-launch timing of the update kernel
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;

@@ -214,7 +214,8 @@ struct ResidentArgs {
     unsigned long long *nclamp_slots;   // [RES_SLOTS] clamp hits per interval of RES_CKPT steps (committed for the
                                         // intervals that stand: an abandoned launch must not count twice)
 };
-constexpr int RES_CKPT = 32;    // steps between checkpoints: an RNG event costs a re-run of 16 steps on average
+constexpr int RES_CKPT = 32;    // steps between checkpoints: an RNG event costs a re-run of 16 steps on average (16-step
+                                // checkpoints were measured: -15 us per event, +20 us per event-free 1000-step frame)
 constexpr int RES_NCKPT = 8;    // checkpoint ring
 constexpr int RES_SLOTS = 64;   // RES_MAX_STEPS / RES_CKPT
 int rowres_strip(int L0, int rows_max);  // sites per thread (8 | 4), 0: shape not eligible

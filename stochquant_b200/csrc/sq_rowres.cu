@@ -596,58 +596,88 @@ __global__ void __launch_bounds__(256) history_sums_kernel(const WelfordArgs A, 
 //     x' = x + (sum_j v_j - n x) / (runs + n):
 // two sums per slice over the launch's steps instead of a sequential recurrence (fp64 rounding differs
 // from the step-by-step form at the 1e-15 level; the parity tolerance on these observables is 1e-3).
-// One thread per slice, loads batched so their latencies overlap; fixed summation order.  (Splitting the
-// step range over four warps per slice block was measured slower.)
-__global__ void __launch_bounds__(128) welford_history_kernel(const WelfordArgs A, const double *step_sums) {
+// A block = 32 slices x 8 step ranges: thread (ts, sg) sums its eighth of the launch's steps for slice ts (a warp's loads of
+// one step are 256 consecutive bytes), the eight partial sums meet in shared memory in fixed order.  One thread per slice
+// over all 1000 steps -- 63 dependent batches of loads -- took 46 us of a 1.9 ms frame; this takes a fifth of it.  One more
+// block sums the per-step global sums the same way.
+constexpr int WELFORD_SG = 8;
+__global__ void __launch_bounds__(256) welford_history_kernel(const WelfordArgs A, const double *step_sums) {
     if (*((volatile const u64 *)A.event_key) != NO_EVENT) return;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const double inv_vs = 1.0 / (double)A.vslice;
+    __shared__ double sh1[WELFORD_SG][32], sh2[WELFORD_SG][32];
+    const int ts = threadIdx.x & 31, sg = threadIdx.x >> 5;
     const double n = (double)A.nsteps, den = (double)(A.runs + A.nsteps);
-    if (t < A.nt) {
-        constexpr int B = 16;
-        double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, last = 0;
-        for (int n0 = 0; n0 < A.nsteps; n0 += B) {
-            double h[B], hm[B];
+    const int chunk = (A.nsteps + WELFORD_SG - 1) / WELFORD_SG;
+    if ((int)blockIdx.x < (A.nt + 31) / 32) {
+        const int t = blockIdx.x * 32 + ts;
+        const int n_lo = min(A.nsteps, sg * chunk), n_hi = min(A.nsteps, n_lo + chunk);
+        double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+        if (t < A.nt) {
+            constexpr int B = 8;
+            for (int n0 = n_lo; n0 < n_hi; n0 += B) {
+                double h[B], hm[B];
 #pragma unroll
-            for (int j = 0; j < B; ++j) {
-                const int k = min(n0 + j, A.nsteps - 1);
-                h[j] = A.hist_rows[(size_t)k * A.nt + t];
-                hm[j] = A.hist_rows[(size_t)k * A.nt + A.tmid];
-            }
-#pragma unroll
-            for (int j = 0; j < B; ++j)
-                if (n0 + j < A.nsteps) {
-                    s1[j & 3] += h[j];
-                    s2[j & 3] = fma(h[j], hm[j], s2[j & 3]);
-                    last = h[j];
+                for (int j = 0; j < B; ++j) {
+                    const int k = min(n0 + j, n_hi - 1);
+                    h[j] = A.hist_rows[(size_t)k * A.nt + t];
+                    hm[j] = A.hist_rows[(size_t)k * A.nt + A.tmid];
                 }
+#pragma unroll
+                for (int j = 0; j < B; ++j)
+                    if (n0 + j < n_hi) {
+                        s1[j & 3] += h[j];
+                        s2[j & 3] = fma(h[j], hm[j], s2[j & 3]);
+                    }
+            }
         }
-        const double SP = ((s1[0] + s1[1]) + (s1[2] + s1[3])) * inv_vs;
-        const double SPP = ((s2[0] + s2[1]) + (s2[2] + s2[3])) * inv_vs * inv_vs;
-        const double x = A.slice_x[t], xx0 = A.slice_xx0[t];
-        A.slice_x[t] = x + (SP - n * x) / den;
-        A.slice_xx0[t] = xx0 + (SPP - n * xx0) / den;
-        A.slice_sum[t] = last;
-    }
-    if (t == A.nt) {  // one spare thread: running means of <phi>, <phi^2>
-        const double inv_vol = 1.0 / ((double)A.vslice * (double)A.nt);
-        double a1 = 0, a2 = 0, s1 = 0, s2 = 0;
-        for (int k = 0; k < A.nsteps; ++k) {
-            s1 = step_sums[2 * k];
-            s2 = step_sums[2 * k + 1];
-            a1 += s1;
-            a2 += s2;
+        sh1[sg][ts] = (s1[0] + s1[1]) + (s1[2] + s1[3]);
+        sh2[sg][ts] = (s2[0] + s2[1]) + (s2[2] + s2[3]);
+        __syncthreads();
+        if (sg == 0 && t < A.nt) {
+            const double inv_vs = 1.0 / (double)A.vslice;
+            double a1 = 0, a2 = 0;
+#pragma unroll
+            for (int g = 0; g < WELFORD_SG; ++g) {
+                a1 += sh1[g][ts];
+                a2 += sh2[g][ts];
+            }
+            const double SP = a1 * inv_vs, SPP = a2 * inv_vs * inv_vs;
+            const double x = A.slice_x[t], xx0 = A.slice_xx0[t];
+            A.slice_x[t] = x + (SP - n * x) / den;
+            A.slice_xx0[t] = xx0 + (SPP - n * xx0) / den;
+            A.slice_sum[t] = A.hist_rows[(size_t)(A.nsteps - 1) * A.nt + t];
         }
-        A.sums[0] = s1;
-        A.sums[1] = s2;
-        A.sums_mean[0] += (a1 * inv_vol - n * A.sums_mean[0]) / den;
-        A.sums_mean[1] += (a2 * inv_vol - n * A.sums_mean[1]) / den;
+    } else {  // the extra block: running means of <phi>, <phi^2> from the per-step global sums
+        double a1 = 0, a2 = 0;
+        for (int k = threadIdx.x; k < A.nsteps; k += 256) {
+            a1 += step_sums[2 * k];
+            a2 += step_sums[2 * k + 1];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+        if (ts == 0) { sh1[sg][0] = a1; sh2[sg][0] = a2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            a1 = 0;
+            a2 = 0;
+            for (int g = 0; g < WELFORD_SG; ++g) {
+                a1 += sh1[g][0];
+                a2 += sh2[g][0];
+            }
+            const double inv_vol = 1.0 / ((double)A.vslice * (double)A.nt);
+            A.sums[0] = step_sums[2 * (A.nsteps - 1)];
+            A.sums[1] = step_sums[2 * (A.nsteps - 1) + 1];
+            A.sums_mean[0] += (a1 * inv_vol - n * A.sums_mean[0]) / den;
+            A.sums_mean[1] += (a2 * inv_vol - n * A.sums_mean[1]) / den;
+        }
     }
 }
 
 cudaError_t launch_welford_history(const WelfordArgs &A, double *step_sums, cudaStream_t stream) {
     history_sums_kernel<<<(A.nsteps + 7) / 8, 256, 0, stream>>>(A, step_sums);
-    welford_history_kernel<<<(A.nt + 1 + 31) / 32, 32, 0, stream>>>(A, step_sums);
+    welford_history_kernel<<<(A.nt + 31) / 32 + 1, 256, 0, stream>>>(A, step_sums);
     return cudaGetLastError();
 }
 
