@@ -69,6 +69,15 @@ struct sq_ctx {
     // the per-CTA partials are double-buffered, events order producer and consumer (sq_api.cu)
     double *l_partials2 = nullptr;
     cudaStream_t fin_stream = nullptr;
+    // sq_frame_host: the field's device -> host copy is enqueued on its own stream right behind the frame's (first) batch of
+    // update kernels -- no host round trip before it starts, and it overlaps the observable kernels; redone if an RNG event
+    // made the batch stop early
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy = nullptr;
+    void *spec_want = nullptr;       // sq_frame_host's destination while its frame is pending
+    void *spec_host = nullptr;       // armed for the batch that completes the frame
+    const void *spec_src = nullptr;  // the device buffer that copy read
+    unsigned batch_seq = 0, spec_batch = 0, ok_batch = 0;  // batches enqueued ; the one the copy followed ; the last one that ran to its end
     cudaEvent_t ev_upd[2] = {nullptr, nullptr}, ev_fin[2] = {nullptr, nullptr};
     int fin_pending = 0;  // finalize launches of the current sequence not yet joined into `stream`
     int cur = 0;

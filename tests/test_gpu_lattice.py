@@ -517,3 +517,29 @@ def test_chain_ensemble_with_jackknife_errors(gpu_sq):
     # chains are independent: the scatter over chains matches each chain's own binned error
     _, e1 = an.binned_error(phi2[:, 0], 10)
     assert 0.3 < e1 / per_chain.std(ddof=1) < 3.0
+
+
+@pytest.mark.parametrize("dims,nsteps", [((256, 96), 40), ((256, 96), 2100), ((32, 8, 8, 8), 6), ((64, 24), 9)])
+def test_frame_host_equals_step_and_download(gpu_sq, oracle, dims, nsteps):
+    """sq_frame_host (host field in, frame, host field out -- the bench's end-to-end call) reads the field back on its own
+    stream right behind the frame's update kernels; the result must be what upload + step + download give, bit for bit:
+    without an event, with an RNG event in the frame (the early copy is void and redone), over several frames, and for a
+    frame longer than one on-chip launch (2100 steps: no early copy)."""
+    V = int(np.prod(dims))
+    rng = np.random.default_rng(41)
+    phi0 = (rng.normal(size=V) * 0.5).astype(np.float32)
+    for seed in (1242608872, seed_with_retry_at(oracle, V // 2 + 3)):
+        a = gpu_sq.Context(dims, real="f32", math="fast", potential=4, m2=0.25, lam=0.5, seed=seed)
+        b = gpu_sq.Context(dims, real="f32", math="fast", potential=4, m2=0.25, lam=0.5, seed=seed)
+        hin, hout = phi0.copy(), np.full(V, np.nan, dtype=np.float32)
+        a.upload(phi0)
+        for _ in range(3):
+            a.step(DTAU, nsteps)
+            want = a.download()
+            ok, _ = b.frame_host(hin.ctypes.data, hout.ctypes.data, DTAU, nsteps)
+            assert ok and np.array_equal(hout, want)
+            hin[:] = hout
+            hout[:] = np.nan
+        assert a.measure()["seed"] == b.measure()["seed"]
+        a.close()
+        b.close()
