@@ -208,7 +208,9 @@ int sq_measure_chains(sq_ctx *ctx, double *mean_phi, double *mean_phi2, uint64_t
 
 /* End-to-end frame through host buffers (the reference's per-frame traffic,
  * tauhost.c:550-554 uploads + :508-515 read-backs): H2D of `host_in` (volume reals),
- * nsteps tau-steps, D2H of the field into `host_out` and of the observables. */
+ * nsteps tau-steps, D2H of the field into `host_out` and of the observables.
+ * Synchronous: `host_out` is complete on return (internally the read-back of a small
+ * field follows the last update kernel on a stream of its own; pin the buffers). */
 int sq_frame_host(sq_ctx *ctx, const void *host_in, void *host_out, int real, double dtau,
                   int nsteps, int64_t runs0, sq_obs *obs, int *stable);
 

@@ -16,11 +16,15 @@
 //     no field data) run while they are in flight.  Their addresses are per-thread 64-bit bases + an immediate
 //     (the row stride is a template parameter for rows of 32 / 64 / 256 sites);
 //   * the LCG is walked in its t2 form (see sq_rowres.cu): two independent 48-bit multiply-adds per site;
-//   * a thread's strip is EIGHT consecutive sites where the row length allows (four otherwise): what is paid per
-//     strip -- the row-to-row advance of the chain, the x0 neighbours, the rare-case tests, the stream addresses --
-//     halves, and the noise phase that covers the global loads' latency doubles.
-// CTA -> tile mapping, jump tables, per-CTA observable partials, clamp slots, replay entries (REBASE), L2
-// chunking and the slab ring's halo protocol are those of the marching kernel, so the host side is shared.
+//   * a thread's strip is four consecutive sites (the template also takes eight: 124 registers, two CTAs per SM, measured
+//     slower and not instantiated);
+//   * what does not depend on the thread is computed once per CTA (TileHdr), what does not depend on the CTA once per
+//     context (TileThread table): a thread's prologue is ~135 instructions instead of ~455;
+//   * the tile's share of the four direct streams is asked into L2 (cp.async.bulk.prefetch.L2) when its copies are issued.
+// CTA -> tile mapping, jump tables, per-tile observable partials, clamp slots, L2 chunking and the slab ring's halo
+// protocol are those of the marching kernel, so the host side is shared; steps that carry replay entries run THERE.
+// Second kernel in this file: lattice_rows_kernel, the row-block staging form (every operand through shared memory,
+// producer warp, tiles claimed from a counter), behind SQ_FLAG_ROWBLOCK_KERNEL -- see its header comment below.
 #include <stdio.h>
 #include <stdlib.h>
 
