@@ -135,6 +135,29 @@ def test_ring_rowblock_kernel_equals_single_context(gpu_sq, oracle, dims, nranks
     assert sum(r["nevents"] for r in res) >= nranks  # every rank replayed the event
 
 
+def test_ring_long_run_equals_single_context_and_oracle(gpu_sq, oracle):
+    """Error growth over a long run on a ring (nothing beyond 25 steps): 3 slabs, 60 + 140 tau-steps in two
+    frames, still IDENTICAL bit for bit to one context -- and that context stays within the per-step tolerance times a
+    modest growth factor of the fp64-noise oracle, seeds bit-exact after 200 steps."""
+    dims = (32, 8, 4, 12)
+    rng = np.random.default_rng(9)
+    phi0 = (rng.normal(size=int(np.prod(dims))) * 0.5).astype(np.float32)
+    kw = dict(real="f32", math="accurate", pot=4, m2=0.25, lam=0.5)
+    whole = gpu_sq.Context(dims, real="f32", math="accurate", potential=4, m2=0.25, lam=0.5)
+    whole.upload(phi0)
+    whole.step(DTAU, 60)
+    whole.step(DTAU, 140)
+    ref, mref = whole.download(), whole.measure()
+    whole.close()
+    res = ring_threads(gpu_sq, 3, dims, phi0, [60, 140], **kw)
+    assert np.array_equal(np.concatenate([r["field"] for r in res]), ref)
+    assert all(r["seed"] == mref["seed"] for r in res)
+    o = oracle.LatticeOracle(dims, real=oracle.F32, potential=4, m2=0.25, lam=0.5, phi0=phi0)
+    o.step(DTAU, 200)
+    assert o.seed == mref["seed"]
+    assert maxabs(ref, o.field) < 20 * ATOL[("f32", "accurate")]
+
+
 def test_multi_process_ring_over_ipc(gpu_sq, oracle, tmp_path):
     """One process per GPU (all GPUs of the box, up to 8), halo arenas mapped through CUDA IPC, NVLink
     peer stores: needs >= 2 GPUs."""
