@@ -945,19 +945,29 @@ bool tile_shape_ok(int ndim, int L0, int L1, int tpr_log, int R, bool rows) {
 template <int MATH, int NDIM, int POT, int L0T>
 static cudaError_t tile_go(const LatticeArgs &A, dim3 grid, size_t smem, cudaStream_t st) {
     if (A.m_on == 3) {
-        int dev = 0, sms = 0, per_sm = 0;
+        // CTAs the device holds at once, per device ordinal and shared-memory size (asked once: the answer does not change;
+        // two host threads asking at the same time write the same numbers)
+        static unsigned slots_of[64] = {0};
+        static size_t smem_of[64] = {0};
+        int dev = 0;
         cudaError_t e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
+        if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
         auto kern = lattice_rows_kernel<MATH, NDIM, POT, L0T>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)) != cudaSuccess) return e;
-        if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 288, smem)) != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        if (slots_of[dev] == 0 || smem_of[dev] != smem) {
+            int sms = 0, per_sm = 0;
+            if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024)) != cudaSuccess) return e;
+            if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 288, smem)) != cudaSuccess) return e;
+            if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+            smem_of[dev] = smem;
+            slots_of[dev] = (unsigned)(sms * per_sm);
+        }
         const unsigned long long nt64 = (unsigned long long)grid.x * grid.y * grid.z;
         if (nt64 >= (1ull << 31) || !A.tile_ctr || !A.rows_thr || A.m_R < 4 || A.m_R % (int)ROWS_D != 0) return cudaErrorInvalidValue;
-        const unsigned ntiles = (unsigned)nt64, slots = (unsigned)(sms * per_sm);
+        const unsigned ntiles = (unsigned)nt64, slots = slots_of[dev];
         const unsigned nb = ntiles < slots ? ntiles : slots;
-        if (getenv("SQ_DEBUG")) fprintf(stderr, "rows: sms %d per_sm %d ntiles %u grid %u smem %zu\n", sms, per_sm, ntiles, nb, smem);
+        if (getenv("SQ_DEBUG")) fprintf(stderr, "rows: slots %u ntiles %u grid %u smem %zu\n", slots, ntiles, nb, smem);
         kern<<<nb, 288, smem, st>>>(A, ntiles, grid.x, (unsigned)((smem - 128) / ROWS_D));
         return cudaGetLastError();
     }
