@@ -104,7 +104,7 @@ extern "C" void sq_free(sq_ctx *c) {
     void *ptrs[] = {c->d_jump, c->c_f, c->c_x, c->c_xx0, c->c_newf, c->c_newx, c->c_newxx0, c->c_omega,
                     c->c_lrgVl, c->c_red, c->c_seed, c->c_nevents, c->c_stable, c->c_lrgEl, c->c_steps, c->c_ctl, c->c_log_rec, c->c_log_xavg,
                     c->l_field[0], c->l_field[1], c->l_ghost[0], c->l_ghost[1], c->l_seeds[0], c->l_seeds[1],
-                    c->l_event, c->l_rebase, c->l_partials, c->l_partials2, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
+                    c->l_event, c->l_rebase, c->l_partials, c->l_slice_sum, c->l_slice_x, c->l_slice_xx0,
                     c->l_sums, c->l_sums_mean, c->l_m2, c->l_lam, c->l_redbuf, c->l_nclamped, c->l_nclamp_step, c->l_slice_jump, c->l_strip_jump, c->l_cta_jump, c->l_thr_jump, c->l_tile_thr, c->l_rows_thr, c->l_tile_ctr,
                     c->r_halo, c->r_error, c->r_progress, c->r_ckpt, c->r_hist_rows, c->r_step_sums, c->r_nclamp_slots};
     for (void *p : ptrs)
@@ -254,8 +254,12 @@ static int init_lattice(sq_ctx *c, const double *f0, uint64_t seed) {
     if ((rc = dalloc(&c->l_event, 1))) return rc;
     if ((rc = dalloc(&c->l_rebase, MAX_REBASE))) return rc;
     const size_t npart = (size_t)p.nchains * c->nt * c->ctas_per_slice * 2;
-    if ((rc = dalloc(&c->l_partials, npart))) return rc;
-    if ((rc = dalloc(&c->l_partials2, npart))) return rc;
+    {   // finalizes are handed to the side stream in groups of fin_batch steps (sq_enqueue_step); SQ_FIN_BATCH=1: per step
+        static const int env_batch = getenv("SQ_FIN_BATCH") ? atoi(getenv("SQ_FIN_BATCH")) : 4;  // A/B knob
+        c->fin_batch = std::min(std::max(env_batch, 1), (int)sq_ctx::FIN_BATCH_MAX);
+        c->npart = npart;
+    }
+    if ((rc = dalloc(&c->l_partials, npart * 2 * (size_t)c->fin_batch))) return rc;
     CK(cudaStreamCreateWithFlags(&c->fin_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
@@ -542,29 +546,45 @@ int sq_launch_update(sq_ctx *c, const LatticeArgs &A) {
     return SQ_OK;
 }
 
+// One step of a launch sequence (k = 0, 1, ... since the last sq_join_finalize).  The update kernels of a group of M steps
+// follow each other in `stream` with nothing in between (the tile kernel's programmatic dependent launch needs that);
+// each writes its per-tile partials into its own buffer of the ring, and the group's finalizes are handed to the side
+// stream together behind the group's last update.  Group g reuses the buffers of group g - 2 and waits for its finalizes.
+static int flush_finalize_group(sq_ctx *c) {
+    if (!c->fin_queued) return SQ_OK;
+    const int pb = c->fin_pending & 1;
+    CK(cudaEventRecord(c->ev_upd[pb], c->stream));
+    CK(cudaStreamWaitEvent(c->fin_stream, c->ev_upd[pb], 0));
+    for (int i = 0; i < c->fin_queued; ++i) {
+        CK(launch_finalize(c->fin_queue[i], c->fin_stream));
+        c->launches++;
+    }
+    CK(cudaEventRecord(c->ev_fin[pb], c->fin_stream));
+    c->fin_queued = 0;
+    c->fin_pending++;
+    return SQ_OK;
+}
+
 int sq_enqueue_step(sq_ctx *c, LatticeArgs &A, FinalizeArgs &F, int k) {
-    const int pb = k & 1;
+    const int M = A.slab_on ? 1 : c->fin_batch;  // (the ring's finder and history need every step's sums at once)
     if (A.partials) {
-        A.partials = pb ? c->l_partials2 : c->l_partials;
+        A.partials = c->l_partials + (size_t)(k % (2 * M)) * c->npart;
         F.partials = A.partials;
-        // the finalize that read this buffer two steps ago must be done before it is overwritten
-        if (c->fin_pending > 1) CK(cudaStreamWaitEvent(c->stream, c->ev_fin[pb], 0));
+        // the finalizes that read this group's buffers two groups ago must be done before they are overwritten
+        if (c->fin_queued == 0 && c->fin_pending > 1) CK(cudaStreamWaitEvent(c->stream, c->ev_fin[c->fin_pending & 1], 0));
     }
     if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     { int rl = sq_launch_update(c, A); if (rl) return rl; }
     if (c->timing) { int rt = sq_timing_mark(c); if (rt) return rt; }
     c->launches++;
     if (A.partials) {
-        CK(cudaEventRecord(c->ev_upd[pb], c->stream));
-        CK(cudaStreamWaitEvent(c->fin_stream, c->ev_upd[pb], 0));
-        CK(launch_finalize(F, c->fin_stream));
-        CK(cudaEventRecord(c->ev_fin[pb], c->fin_stream));
-        c->launches++;
-        c->fin_pending++;
+        c->fin_queue[c->fin_queued++] = F;
+        if (c->fin_queued >= M) return flush_finalize_group(c);
     }
     return SQ_OK;
 }
 int sq_join_finalize(sq_ctx *c) {
+    { int rf = flush_finalize_group(c); if (rf) return rf; }
     if (c->fin_pending > 0) {
         CK(cudaStreamWaitEvent(c->stream, c->ev_fin[0], 0));
         if (c->fin_pending > 1) CK(cudaStreamWaitEvent(c->stream, c->ev_fin[1], 0));

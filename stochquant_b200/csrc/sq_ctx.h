@@ -65,9 +65,15 @@ struct sq_ctx {
            *l_sums = nullptr, *l_sums_mean = nullptr, *l_m2 = nullptr, *l_lam = nullptr, *l_redbuf = nullptr;
     unsigned long long *l_nclamped = nullptr;
     unsigned long long *l_nclamp_step = nullptr;  // [MAX_SEQ_STEPS] clamp hits per step of the sequence in flight
-    // observables off the critical path: finalize(n) runs on a side stream while update(n+1) runs;
-    // the per-CTA partials are double-buffered, events order producer and consumer (sq_api.cu)
-    double *l_partials2 = nullptr;
+    // observables off the critical path: the finalizes of a GROUP of fin_batch steps run on a side stream while the next
+    // group's updates run; l_partials is a ring of 2 * fin_batch per-step buffers of npart doubles, events order producer
+    // and consumer per group (sq_api.cu: sq_enqueue_step).  Inside a group nothing sits between two update kernels in
+    // `stream`, so the tile kernel's programmatic dependent launch overlaps them.
+    static constexpr int FIN_BATCH_MAX = 8;
+    int fin_batch = 1;
+    size_t npart = 0;
+    sq::FinalizeArgs fin_queue[FIN_BATCH_MAX];
+    int fin_queued = 0;
     cudaStream_t fin_stream = nullptr;
     // sq_frame_host: the field's device -> host copy is enqueued on its own stream right behind the frame's (first) batch of
     // update kernels -- no host round trip before it starts, and it overlaps the observable kernels; redone if an RNG event
@@ -79,7 +85,7 @@ struct sq_ctx {
     const void *spec_src = nullptr;  // the device buffer that copy read
     unsigned batch_seq = 0, spec_batch = 0, ok_batch = 0;  // batches enqueued ; the one the copy followed ; the last one that ran to its end
     cudaEvent_t ev_upd[2] = {nullptr, nullptr}, ev_fin[2] = {nullptr, nullptr};
-    int fin_pending = 0;  // finalize launches of the current sequence not yet joined into `stream`
+    int fin_pending = 0;  // finalize GROUPS of the current sequence handed to the side stream and not yet joined into `stream`
     int cur = 0;
     int nt = 0, ctas_per_slice = 1;
     int64_t vslice = 0, V = 0, vlocal = 0;

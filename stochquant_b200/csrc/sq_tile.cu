@@ -984,12 +984,13 @@ static cudaError_t tile_go(const LatticeArgs &A, dim3 grid, size_t smem, cudaStr
         cudaError_t e = cudaFuncSetAttribute(lattice_tile_kernel<MATH, NDIM, POT, L0T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
         if (e != cudaSuccess) return e;
     }
-    // Programmatic dependent launch pays only where nothing sits between two steps' update kernels in the stream: with
-    // observables on, the event the finalize stream waits for is recorded there and the overlap never happens (measured on
-    // 64^4: 56.9 -> 56.7 us per step with observables, 54.3 -> 50.7 with SQ_FLAG_NO_OBSERVABLES).  Fusing the per-step
-    // reduction into the update kernel's last tile per slice is what would carry the 6.5 % over to the default path.
+    // Programmatic dependent launch pays only where nothing sits between two steps' update kernels in the stream.  With
+    // observables on, the events that order the finalize stream used to be recorded there (64^4: 56.9 -> 56.7 us per step
+    // with observables, 54.3 -> 50.7 with SQ_FLAG_NO_OBSERVABLES); sq_enqueue_step now hands the finalizes over in groups
+    // of fin_batch steps, so the update kernels inside a group are neighbours in the stream.  Everything this kernel reads
+    // or writes that another launch touches (field, seed, event word, partials) sits behind its griddepcontrol.wait.
     static const bool pdl_env = !(getenv("SQ_PDL") && atoi(getenv("SQ_PDL")) == 0);  // A/B knob
-    const bool pdl = pdl_env && !A.partials && !A.slab_on;
+    const bool pdl = pdl_env && !A.slab_on;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(256);

@@ -543,3 +543,39 @@ def test_frame_host_equals_step_and_download(gpu_sq, oracle, dims, nsteps):
         assert a.measure()["seed"] == b.measure()["seed"]
         a.close()
         b.close()
+
+
+_GROUPING_SCRIPT = r"""
+import hashlib, sys
+import numpy as np
+import stochquant_b200 as sq
+ctx = sq.Context((32, 16, 8, 16), real="f32", math="fast")
+h = hashlib.sha256()
+for n in (37, 5, 1, 8):   # odd sequence lengths: partial groups, the join at the end of a sequence
+    ctx.step(0.01, n)
+    m = ctx.measure()
+    h.update(ctx.download().tobytes())
+    for k in ("slice_x", "slice_xx0", "corr"):
+        h.update(np.ascontiguousarray(m[k]).tobytes())
+    h.update(repr((m["seed"], m["mean_phi"], m["mean_phi2"], m["runs"], m["nclamped"])).encode())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_finalize_grouping_and_dependent_launch_change_nothing(gpu_sq):
+    """sq_enqueue_step hands the per-step finalize kernels to the side stream in groups of SQ_FIN_BATCH steps (default 4) so
+    that the update kernels of a group are neighbours in the stream and overlap by programmatic dependent launch.  That
+    only moves work between streams: field, seed and every running mean must be bit-identical to the per-step hand-over
+    without dependent launches.  The knobs are read once per process, hence the subprocesses."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for name, env in (("default", {}), ("per_step", {"SQ_FIN_BATCH": "1", "SQ_PDL": "0"}), ("groups_of_8", {"SQ_FIN_BATCH": "8"})):
+        e = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), **env)
+        for k in ("SQ_FIN_BATCH", "SQ_PDL"):
+            if k not in env:
+                e.pop(k, None)
+        r = subprocess.run([sys.executable, "-c", _GROUPING_SCRIPT], env=e, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[name] = [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][0]
+    assert digests["default"] == digests["per_step"] == digests["groups_of_8"], digests
