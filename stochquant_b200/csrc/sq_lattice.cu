@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256, (REBASE || NDIM == 4 || sizeof(real) == 8
 // (tau_kernel.cl:144-145 at time-slice granularity; the host's xavg is derived in sq_measure)
 __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs A) {
     extern __shared__ double ssum[];  // [nt] slice sums, then [nt] phi^2 sums
-    // This runs on a side stream beside update(step_index + 1): an event raised by a LATER step must not
+    // This runs on a side stream beside the updates of later steps (sq_enqueue_step): an event raised by a LATER step must not
     // drop this step's sample (the host keeps every step before the event step); only the event step
     // itself and the launches behind it are void.
     const u64 key = *((volatile const u64 *)A.event_key);
