@@ -19,7 +19,7 @@ OpenMP port timed on the host cores on a bounded sample of the same workload.
 
 Beyond the contract's keys the default line carries
   `extras`  (N = 1) the other BASELINE configs measured in the same run: `accurate` (c2 with
-            SQ_MATH_ACCURATE), `c3` (64^4), `c5` (64 of the 512-chain share), `c1` (the drop-in
+            SQ_MATH_ACCURATE), `c2phi4_fast` (c2 with the phi^4 force), `c3` (64^4), `c5` (64 of the 512-chain share), `c1` (the drop-in
             ./tauhost.o on the reference's default command line, shortened);
   `ring`    (N > 1) configs[3]: ONE 256^4 lattice in N time slabs with the halos moving over NVLink
             inside the update kernel -- strong-scaling value, the same slab volume as a ring of one
@@ -712,7 +712,9 @@ def main():
             extras = {}
             k = max(3, min(args.steps, 5))
             # c2 with the reference's casts and CUDA's logf/cosf/sqrtf (SQ_MATH_ACCURATE)
-            for wname, math, nch in (("c2", "accurate", None), ("c3", "fast", None), ("c3", "accurate", None), ("c5", "fast", 64)):
+            # ... and with the phi^4 force (BASELINE configs[1] says "phi^4": SURVEY 8(d) C2 fixes potID 0 with this as its variant)
+            for wname, math, nch in (("c2", "accurate", None), ("c2phi4", "fast", None), ("c3", "fast", None), ("c3", "accurate", None),
+                                     ("c5", "fast", 64)):
                 w = dict(WORKLOADS[wname])
                 if math == args.math and wname == name:
                     continue
