@@ -221,3 +221,44 @@ def test_free_field_statistics(oracle):
     lam = 4 * np.sin(k0[:, None] / 2) ** 2 + 4 * np.sin(k1[None, :] / 2) ** 2 + 2.0
     want = float(np.mean(1.0 / (lam * (1 - eps * lam / 2))))
     assert abs(acc / n - want) < 0.03 * want
+
+
+@pytest.mark.parametrize("a", [1.0, 0.5, 0.25, 2.0])
+@pytest.mark.parametrize("real", ["f64", "f32"])
+def test_lattice_definition_reduces_to_the_reference_kernel_in_1d(oracle, a, real):
+    """The d-dimensional update has no reference code; its DEFINITION (sqo_lattice_step) is pinned
+    here to the reference kernel: a 1 x N lattice (one site per time slice, the x0 neighbours are the site itself) is the
+    reference's chain away from its ends -- same shared-seed draw per site (gid = t, the omega item's draw at gid = N), same
+    Box-Muller, same Euler step (tau_kernel.cl:114 with potID 0: W = 2, clas = 0).  Compared with the restatement of
+    time_dev (bit-equal to the reference's own source by the tests above) and, where oracle/_ref exists, with that
+    source itself.  The two differ only (i) at the ends (reference: fixed ghosts, lattice: periodic), which move inwards
+    one site per step -- the comparison keeps clear of them -- and (ii) in the noise amplitude, sqrt(2 dtau / a^d) with
+    d = 2 here against d = 1, undone through C = sqrt(a) up to the float rounding of the amplitude.  Observables: the
+    slice means of a 1 x N lattice are the reference's x_i and xx0_i (:144-145)."""
+    N, dtau, K, seed = 200, 0.002, 20, 1242608872
+    f0 = 0.1 * np.random.default_rng(7).standard_normal(N)
+    if real == "f32":
+        f0 = f0.astype(np.float32).astype(np.float64)
+    chains = [oracle.Compat1D(N, a, dtau, 0, 1.0, f0, 0.0, seed)]
+    if oracle.ref_available():
+        chains.append(oracle.RefKernel(N, a, dtau, 0, 1.0, f0, 0.0, seed))
+    lat = oracle.LatticeOracle((1, N), real=oracle.F64 if real == "f64" else oracle.F32, potential=0, a=a,
+                               c=float(np.sqrt(a)), seed=seed, phi0=f0)
+    for _ in range(K):
+        lat.step(dtau)
+        for c in chains:
+            if isinstance(c, oracle.Compat1D):
+                assert c.frame(1)
+                assert c.s.rand1 == lat.seed            # the integer stream: bit-exact, step by step
+            else:
+                assert c.steps_canonical(1)
+                assert c.rand1.value == lat.seed
+    lo, hi = K + 2, N - K - 2
+    # fp64: one rounding of the amplitude in float (2^-24 relative of a noise term ~0.1 per step); fp32 storage: 2^-24 of phi per step
+    tol = 2e-7 if real == "f64" else 2e-5
+    for c in chains:
+        assert np.abs(lat.field[lo:hi].astype(np.float64) - c.f[lo:hi]).max() < tol
+        assert np.abs(lat.slice_x[lo:hi] - c.x[lo:hi]).max() < tol
+        assert np.abs(lat.slice_xx0[lo:hi] - c.xx0[lo:hi]).max() < tol
+    if a in (1.0, 0.25) and real == "f64":  # amplitudes that are exact in float: equal to the last bit or two
+        assert np.abs(lat.field[lo:hi] - chains[0].f[lo:hi]).max() < 1e-15
