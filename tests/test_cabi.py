@@ -90,3 +90,34 @@ def test_lcg_jump_host_utility(sq, oracle):
         if g % 211 == 0:
             assert L.sq_lcg_jump(1242608872, 0, g) == (s.value & (2**48 - 1))
         oracle.lib().sqo_random(C.byref(s), g, None)
+
+
+def test_rng_resolve_against_the_survey_kats(sq, oracle):
+    """sq_rng_resolve is the PRODUCT's literal replay of one draw (the host side of every RNG-event recovery and of the
+    ring's agreement, tau_kernel.cl:269-284 incl. the do/while retry and the `seed +=` branch).  Pinned here, without a
+    GPU, to SURVEY.md 8(c) G1 -- the same integers the oracle is pinned to -- and to the oracle on random inputs."""
+    def at(seed, gid):  # the draw at `gid` from `seed`: an entry that says "draws at gid >= gid continue from seed"
+        e = {"gid_start": gid, "seed": seed, "ov_gid": 2**64 - 1, "ov_t1": 0, "ov_t2": 0}
+        return sq.rng_resolve(0, [e] if gid else [], gid) if gid else sq.rng_resolve(seed, [], 0)
+    plain = [(1242608872, 0, 0x8f7a818576d3, 0x9dba931929e2, 173422509894114),
+             (1242608872, 1, 0x8f8060725d40, 0x58e126661ab8, 97721887627960),
+             (1242608872, 200, 0x9410aa997bfb, 0xd3dda7355112, 232946799038738),
+             (1, 0, 0x5deece678, 0xbb61488df123, 206024356000035),
+             (2**64 - 5, 7, 0xbbdd9cce5, 0x76ab15684887, 130475023157383)]
+    for s, g, t1, t2, nx in plain:
+        e, nd, plus = at(s, g)
+        assert (e["ov_gid"], e["ov_t1"], e["ov_t2"], e["seed"], e["gid_start"], nd, plus) == (g, t1, t2, nx, g + 1, 1, 0)
+    for s, g, t1, t2, nx in [(1760221443, 3, 277355843144601, 121207, 1760342650), (668289095, 3, 64439088464781, 140379, 668429474)]:
+        e, nd, plus = at(s, g)   # `*seed += temp` (:278-279)
+        assert (e["ov_t1"], e["ov_t2"], e["seed"], nd, plus) == (t1, t2, nx, 1, 1)
+    for s, g, t1, t2, nx in [(177446488061229, 0, 0xdc5d786b660e, 0xf1c4fc530801, 0xf1c47c530801),
+                             (177446488061224, 5, 0x841e58ec1a3c, 0xc0818e0993b8, 0xc0810e0993b8)]:
+        e, nd, plus = at(s, g)   # inf-retry (:282): the first t1 is 0x1234, the draw is repeated from the updated seed
+        assert (e["ov_t1"], e["ov_t2"], e["seed"], nd) == (t1, t2, nx, 2)
+    import random
+    rnd = random.Random(5)
+    for _ in range(2000):
+        s, g = rnd.getrandbits(rnd.choice([20, 31, 48, 64])), rnd.getrandbits(rnd.choice([1, 8, 20, 33]))
+        e, nd, plus = at(s, g)
+        _, rec = oracle.random(s, g)
+        assert (e["ov_t1"], e["ov_t2"], e["seed"], nd, plus) == (rec.t1, rec.t2, rec.seed_after, rec.ndraws, rec.plus_branch)
