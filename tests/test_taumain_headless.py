@@ -57,3 +57,56 @@ open(a[11], 'w').write('end file placeholder\\n')
     got = np.array(rep["last_y"])
     assert any(np.array_equal(np.nan_to_num(got, nan=-1e300, neginf=-1e308), np.nan_to_num(y, nan=-1e300, neginf=-1e308)) for y in ys)
     assert (tmp_path / "V0_2e_0-8.txt").exists()
+
+
+TAUMAIN_WIN = "/root/reference/taumain_windows.py"
+# what taumain_windows.py:163 passes for its selected preset (`double_well`, :14, :129-160):
+# n, deltat, deltatau, h, parisi, entw, potID, c, device, rpf, intime, loops, inputf, outputf, acco
+WIN_ARGV = ['100', '1.0', '0.01', '1e-05', '0', '100', '3', '1.0', '0', '1', '0', '10000', '0', '0', '40']
+
+
+@pytest.mark.skipif(not os.path.exists(TAUMAIN_WIN), reason="the reference front-end is only present in the build container")
+def test_unmodified_taumain_windows_runs_headless_with_its_15_arguments(tmp_path):
+    """The other front-end north_star names: /root/reference/taumain_windows.py, run where it lies, unmodified.  It spawns
+    `tauhost.exe` (looked up on PATH) with FIFTEEN positional arguments (:163), reads stdout byte by byte (:33) and plots
+    from a thread (:60-97).  The stand-in `tauhost.exe` checks that argv, and -- as there is no GPU here -- writes the
+    frame stream of the same run with 20 instead of 10000 tau-steps per frame through the CPU restatement of the
+    reference host (oracle.tauhost_main; same line format as the drop-in, tests/test_host_io.py).  That the REAL drop-in
+    accepts exactly this argv is asserted on its parser: without a GPU it gets as far as sq_init and exits 3, not 2."""
+    stream = tmp_path / "stream.txt"
+    fake = tmp_path / "tauhost.exe"
+    fake.write_text(f"""#!{sys.executable}
+import sys, time
+sys.path.insert(0, {ROOT!r})
+a = sys.argv[1:]
+assert a == {WIN_ARGV!r}, a
+from oracle import oracle as O
+n, dt, dtau, h, parisi, frames, pot, c, dev, fps, intime, loops, fin, fout, acc = a
+assert O.tauhost_main([n, dt, dtau, frames, pot, c, dev, fps, intime, '20', fin, fout, acc], {str(stream)!r}) == 0
+for line in open({str(stream)!r}, 'rb'):
+    sys.stdout.buffer.write(line)
+    sys.stdout.buffer.flush()
+    time.sleep(0.002)
+""")
+    fake.chmod(fake.stat().st_mode | stat.S_IXUSR)
+    report = tmp_path / "report.json"
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tests", "stubs"), SQ_MPL_STUB_REPORT=str(report),
+               SQ_MPL_STUB_TIMEOUT="120", PATH=str(tmp_path) + os.pathsep + os.environ.get("PATH", ""))
+    r = subprocess.run([sys.executable, TAUMAIN_WIN], cwd=str(tmp_path), env=env, capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    assert "100.00%, " in r.stdout.decode()                       # taumain_windows.py:56: the data thread saw EOF and left
+    lines = open(stream, "rb").read().splitlines()
+    assert len(lines) == 100                                     # entw frames, rpf = 1
+    rep = json.loads(report.read_text())
+    assert rep["npoints"] == 99 and rep["ylim"] == [-15.0, 15.0]  # :174 (range(n-1)), :160 (theoVal 10 -> dmax 15)
+    assert rep["distinct_frames"] >= 2
+    ys = [np.genfromtxt([l.strip().decode()], delimiter="|")[:-2] for l in lines]
+    got = np.array(rep["last_y"])
+    assert any(np.array_equal(np.nan_to_num(got, nan=-1e300, neginf=-1e308), np.nan_to_num(y, nan=-1e300, neginf=-1e308)) for y in ys)
+    # the drop-in's own parser takes this argv (15-argument form: h ignored, parisi = 0) and only then looks for a GPU
+    exe = os.path.join(ROOT, "tauhost.o")
+    if os.path.exists(exe):
+        import stochquant_b200 as sq
+        if sq.load().sq_device_count() <= 0:
+            rr = subprocess.run([exe] + WIN_ARGV, capture_output=True, text=True, timeout=120)
+            assert rr.returncode == 3 and rr.stdout == "" and "usage" not in rr.stderr, (rr.returncode, rr.stderr)
