@@ -55,8 +55,9 @@ def test_traffic_file_shape(bench):
 
 
 def test_committed_bench_lines_keep_the_contract():
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench", "bench_*.json")))
-    assert files
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench", "bench_*.json")) +
+                   glob.glob(os.path.join(ROOT, "profiles", "r02_bench", "headcheck_bench_*.json")))
+    assert len(files) > 20
     for f in files:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
@@ -65,5 +66,9 @@ def test_committed_bench_lines_keep_the_contract():
         assert d["vs_baseline"] is None and d["config"]["workload"]
         if d.get("impl") == "reference":
             assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
+        if d.get("impl") != "reference" and d["n_gpus"] == 1 and d["config"]["workload"] in ("c2", "c3", "slab", "c5"):
+            r = d["roofline"]   # the GPU arm's line: roofline object, clocks, launches of our own kernels
+            assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] < 1
+            assert d["gpu_launches"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
         if d["n_gpus"] > 1 and d["config"]["workload"] == "c2":
             assert d["ring"]["ring_parity"] == "bit-identical" and d["ring_parity"] == "bit-identical"
